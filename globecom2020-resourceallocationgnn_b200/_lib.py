@@ -1,0 +1,114 @@
+"""ctypes binding of the C-ABI in include/v2v_gnn.h.
+
+There is no CPU or eager-PyTorch fallback: if the shared library cannot be
+loaded (and cannot be built because nvcc is absent) importing any compute entry
+point raises, loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_LIB = None
+
+c_float_p = C.POINTER(C.c_float)
+c_u32_p = C.POINTER(C.c_uint32)
+c_i32_p = C.POINTER(C.c_int32)
+c_void_p = C.c_void_p
+
+
+class BrainConfig(C.Structure):
+    """Mirror of ``v2v_brain_config`` (include/v2v_gnn.h)."""
+    _fields_ = [
+        ("num_d2d", C.c_int), ("node_dim", C.c_int), ("edge_dim", C.c_int), ("feedback", C.c_int),
+        ("num_ch", C.c_int), ("stages", C.c_int), ("per_slot", C.c_int), ("hidden", C.c_int * 3),
+        ("max_batch", C.c_int), ("dtype", C.c_int),
+        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+    ]
+
+
+# name -> (restype, argtypes).  Every symbol include/v2v_gnn.h declares is listed here;
+# tests/test_capi_symbols.py checks the two stay in sync.
+SIGNATURES = {
+    "v2v_last_error": (C.c_char_p, []),
+    "v2v_version": (C.c_int, []),
+    "v2v_device_sm_count": (C.c_int, []),
+    "v2v_adj_pack_masks": (C.c_int, [c_void_p, C.c_int, C.c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "v2v_agg_mask": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
+    "v2v_agg_dense": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
+    "v2v_dense_fwd": (C.c_int, [C.c_int, C.POINTER(c_void_p), C.POINTER(C.c_int), c_void_p, C.c_int, c_void_p,
+                                c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
+    "v2v_dense_bwd_data": (C.c_int, [c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, c_void_p, C.c_int,
+                                     C.c_int, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
+    "v2v_dense_bwd_weight": (C.c_int, [C.c_int, C.POINTER(c_void_p), C.POINTER(C.c_int), c_void_p, c_void_p,
+                                       c_void_p, C.c_int, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
+    "v2v_huber_loss_grad": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int,
+                                      C.c_float, c_void_p]),
+    "v2v_td_target": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_float, c_void_p, C.c_int, C.c_int,
+                                C.c_int, c_void_p]),
+    "v2v_adam_step": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_long, C.c_int, C.c_float, C.c_float,
+                                C.c_float, C.c_float, C.c_float, c_void_p]),
+    "v2v_brain_create": (C.c_int, [C.POINTER(BrainConfig), C.POINTER(c_void_p)]),
+    "v2v_brain_destroy": (None, [c_void_p]),
+    "v2v_brain_param_count": (C.c_long, [c_void_p]),
+    "v2v_brain_get_params": (C.c_int, [c_void_p, C.c_int, c_void_p, c_void_p]),
+    "v2v_brain_set_params": (C.c_int, [c_void_p, C.c_int, c_void_p, c_void_p]),
+    "v2v_brain_param_ptr": (c_void_p, [c_void_p, C.c_int]),
+    "v2v_brain_update_target": (C.c_int, [c_void_p, c_void_p]),
+    "v2v_brain_get_iterations": (C.c_int, [c_void_p]),
+    "v2v_brain_set_iterations": (C.c_int, [c_void_p, C.c_int]),
+    "v2v_brain_forward": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, c_void_p,
+                                    c_void_p]),
+    "v2v_brain_forward_backward": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             C.c_int, c_void_p, c_void_p]),
+    "v2v_brain_apply_adam": (C.c_int, [c_void_p, C.c_float, c_void_p]),
+    "v2v_brain_train_step": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       C.c_int, c_void_p, c_void_p]),
+    "v2v_brain_predict_host": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, c_void_p,
+                                         c_void_p]),
+    "v2v_brain_train_host": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, c_void_p,
+                                       c_void_p]),
+}
+
+
+class V2VError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building first if the .so is absent and nvcc exists). Never falls back."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        _build.build()
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)       # AttributeError if the library lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def check(rc: int, exc=V2VError):
+    if rc != 0:
+        msg = load().v2v_last_error()
+        raise exc(msg.decode() if msg else f"v2v error {rc}")
+
+
+def ptr(t):
+    """Device/host pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

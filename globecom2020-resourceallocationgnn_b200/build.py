@@ -1,0 +1,84 @@
+"""In-tree build of the sm_100a shared library (nvcc, no torch headers needed).
+
+``python globecom2020-resourceallocationgnn_b200/build.py`` or ``__graft_entry__.build()``.
+The .so stays next to this file so that it travels with the repo snapshot to the GPU box.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_NAME = "libv2vgnn_b200.so"
+LIB_PATH = os.path.join(HERE, LIB_NAME)
+SOURCES = ["agg.cu", "dense.cu", "loss_opt.cu", "brain.cu"]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "--use_fast_math=false" if False else "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fvisibility=default",
+    "--expt-relaxed-constexpr",
+]
+
+
+def nvcc_path() -> str:
+    cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(cand):
+        raise RuntimeError("nvcc not found; the V2V GNN engine has no CPU fallback")
+    return cand
+
+
+def sources():
+    out = [os.path.join(CSRC, s) for s in SOURCES]
+    extra = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu") and f not in SOURCES)
+    return out + [os.path.join(CSRC, f) for f in extra]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps.append(os.path.join(HERE, "..", "include", "v2v_gnn.h"))
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB_PATH
+    objs = []
+    procs = []
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    for src in sources():
+        obj = os.path.join(HERE, "build", os.path.basename(src) + ".o")
+        cmd = [nvcc_path(), *NVCC_FLAGS, "-c", src, "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+            print(" ".join(cmd), flush=True)
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            failed = True
+            sys.stderr.write(f"--- nvcc failed for {src} ---\n{out}\n")
+        elif verbose and out:
+            print(out)
+    if failed:
+        raise RuntimeError("nvcc compilation failed")
+    link = [nvcc_path(), "-shared", "-o", LIB_PATH + ".tmp", *objs,
+            "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+    r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout)
+    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

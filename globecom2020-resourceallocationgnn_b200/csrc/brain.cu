@@ -1,0 +1,383 @@
+// The brain: BS._create_model / train_dnn / predict / update_target_model
+// (BS_brain.py:90-239) as a stream-ordered sequence of the engine's kernels.
+//
+// Wiring (BS_brain.py:147-200), S = number of GNN stages, last stage linear:
+//   h0 = act([node|edge] . W0[:Dn+De])              (third input is zeros, :478/:589)
+//   a0 = Agg(h0)
+//   hs = act([h(s-1)|node|edge|a(s-1)] . Ws), as = Agg(hs)          s = 1..S-1
+//   z  = [node | h(S-1) | a(S-1)] -> Dense 80 relu, 40 relu, 20 relu, CH linear
+// Loss: per-head mean Huber, heads summed (:86-87, :214).  Optimiser: Keras Adam (:212).
+#include <math.h>
+#include <stdarg.h>
+#include <vector>
+
+#include "v2v_common.cuh"
+
+namespace v2v {
+
+std::string& last_error() {
+  static thread_local std::string e;
+  return e;
+}
+
+int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  return 1;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
+    n = p.multiProcessorCount;
+  }
+  return n;
+}
+
+struct LayerDesc {
+  int K, n_out;       // stacked weight rows / columns
+  size_t w_off, b_off;  // offsets (floats) into a parameter set
+};
+
+}  // namespace v2v
+
+using namespace v2v;
+
+struct v2v_brain {
+  v2v_brain_config cfg;
+  int N, Dn, De, F, CH, S, G, n_layers;
+  std::vector<LayerDesc> layers;
+  size_t n_params = 0;
+  int iterations = 0;
+  // device memory
+  float* params[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // online, target, grad, m, v
+  std::vector<float*> h, agg;     // per stage [maxB][N][F]
+  std::vector<float*> mlp;        // per MLP layer output [maxB][N][n_out]
+  std::vector<float*> dmlp;       // gradient w.r.t. MLP layer *inputs* (gated), index j: input of layer j (j>=1)
+  float* dq = nullptr;
+  float* dh_a = nullptr;
+  float* dh_b = nullptr;
+  float* dagg = nullptr;
+  float* head_loss = nullptr;     // [N]
+  // staging for the host-buffer entry points
+  float* st_node = nullptr; float* st_edge = nullptr; float* st_neigh = nullptr; float* st_adj = nullptr; float* st_y = nullptr;
+  float* st_q = nullptr;
+  uint32_t* st_in_mask = nullptr; uint32_t* st_out_mask = nullptr;
+  int* st_flag = nullptr;
+  int* st_flag_host = nullptr;    // pinned
+};
+
+static int dmalloc(float** p, size_t n_floats) {
+  V2V_CHECK_CUDA(cudaMalloc((void**)p, std::max<size_t>(n_floats, 1) * sizeof(float)));
+  return 0;
+}
+
+extern "C" const char* v2v_last_error(void) { return last_error().c_str(); }
+extern "C" int v2v_version(void) { return 100; }
+extern "C" int v2v_device_sm_count(void) { return sm_count(); }
+
+extern "C" void v2v_brain_destroy(v2v_brain* b) {
+  if (!b) return;
+  for (auto& p : b->params) cudaFree(p);
+  for (auto p : b->h) cudaFree(p);
+  for (auto p : b->agg) cudaFree(p);
+  for (auto p : b->mlp) cudaFree(p);
+  for (auto p : b->dmlp) cudaFree(p);
+  cudaFree(b->dq); cudaFree(b->dh_a); cudaFree(b->dh_b); cudaFree(b->dagg); cudaFree(b->head_loss);
+  cudaFree(b->st_node); cudaFree(b->st_edge); cudaFree(b->st_neigh); cudaFree(b->st_adj); cudaFree(b->st_y); cudaFree(b->st_q);
+  cudaFree(b->st_in_mask); cudaFree(b->st_out_mask); cudaFree(b->st_flag);
+  if (b->st_flag_host) cudaFreeHost(b->st_flag_host);
+  delete b;
+}
+
+extern "C" int v2v_brain_create(const v2v_brain_config* cfg, v2v_brain** out) {
+  V2V_REQUIRE(cfg && out, "v2v_brain_create: null argument");
+  V2V_REQUIRE(cfg->num_d2d >= 1 && cfg->num_d2d <= 256, "v2v_brain_create: num_d2d=%d out of range [1,256]", cfg->num_d2d);
+  V2V_REQUIRE(cfg->node_dim > 0 && cfg->edge_dim > 0 && cfg->feedback > 0 && cfg->num_ch > 0, "v2v_brain_create: non-positive dimension");
+  V2V_REQUIRE(cfg->stages >= 1 && cfg->stages <= 8, "v2v_brain_create: stages=%d out of range [1,8]", cfg->stages);
+  V2V_REQUIRE(cfg->max_batch >= 1, "v2v_brain_create: max_batch must be >= 1");
+  V2V_REQUIRE(cfg->dtype == V2V_F32, "v2v_brain_create: only V2V_F32 activations are implemented in the brain");
+  for (int i = 0; i < 3; ++i) V2V_REQUIRE(cfg->hidden[i] > 0, "v2v_brain_create: hidden[%d] must be > 0", i);
+  v2v_brain* b = new v2v_brain();
+  b->cfg = *cfg;
+  b->N = cfg->num_d2d; b->Dn = cfg->node_dim; b->De = cfg->edge_dim; b->F = cfg->feedback;
+  b->CH = cfg->num_ch; b->S = cfg->stages; b->G = cfg->per_slot ? cfg->num_d2d : 1;
+  size_t off = 0;
+  auto add_layer = [&](int K, int n_out) {
+    LayerDesc L;
+    L.K = K; L.n_out = n_out;
+    L.w_off = off; off += (size_t)b->G * K * n_out;
+    L.b_off = off; off += (size_t)b->G * n_out;
+    b->layers.push_back(L);
+  };
+  for (int s = 0; s < b->S; ++s) add_layer((s == 0 ? b->Dn : b->F + b->Dn) + b->De + b->F, b->F);
+  int k = b->Dn + 2 * b->F;
+  for (int i = 0; i < 3; ++i) { add_layer(k, cfg->hidden[i]); k = cfg->hidden[i]; }
+  add_layer(k, b->CH);
+  b->n_layers = (int)b->layers.size();
+  b->n_params = off;
+
+  const size_t mb = (size_t)cfg->max_batch, rows = mb * b->N;
+  int rc = 0;
+  for (auto& p : b->params) rc |= dmalloc(&p, b->n_params);
+  b->h.resize(b->S); b->agg.resize(b->S);
+  for (int s = 0; s < b->S; ++s) { rc |= dmalloc(&b->h[s], rows * b->F); rc |= dmalloc(&b->agg[s], rows * b->F); }
+  b->mlp.resize(4); b->dmlp.resize(4, nullptr);
+  for (int j = 0; j < 4; ++j) {
+    rc |= dmalloc(&b->mlp[j], rows * b->layers[b->S + j].n_out);
+    if (j >= 1) rc |= dmalloc(&b->dmlp[j], rows * b->layers[b->S + j].K);
+  }
+  rc |= dmalloc(&b->dq, rows * b->CH);
+  rc |= dmalloc(&b->dh_a, rows * b->F); rc |= dmalloc(&b->dh_b, rows * b->F); rc |= dmalloc(&b->dagg, rows * b->F);
+  rc |= dmalloc(&b->head_loss, b->N);
+  rc |= dmalloc(&b->st_node, rows * b->Dn); rc |= dmalloc(&b->st_edge, rows * b->De); rc |= dmalloc(&b->st_neigh, rows * b->F);
+  rc |= dmalloc(&b->st_adj, rows * b->N); rc |= dmalloc(&b->st_y, rows * b->CH); rc |= dmalloc(&b->st_q, rows * b->CH);
+  const int W = ceil_div(b->N, 32);
+  if (cudaMalloc((void**)&b->st_in_mask, rows * W * 4) != cudaSuccess) rc = 1;
+  if (cudaMalloc((void**)&b->st_out_mask, rows * W * 4) != cudaSuccess) rc = 1;
+  if (cudaMalloc((void**)&b->st_flag, sizeof(int)) != cudaSuccess) rc = 1;
+  if (cudaMallocHost((void**)&b->st_flag_host, sizeof(int)) != cudaSuccess) rc = 1;
+  if (rc) {
+    std::string e = last_error();
+    v2v_brain_destroy(b);
+    return fail("v2v_brain_create: device allocation failed (%s)", e.c_str());
+  }
+  for (auto& p : b->params) cudaMemset(p, 0, b->n_params * sizeof(float));
+  *out = b;
+  return 0;
+}
+
+extern "C" long v2v_brain_param_count(const v2v_brain* b) { return b ? (long)b->n_params : -1; }
+extern "C" float* v2v_brain_param_ptr(v2v_brain* b, int which) {
+  return (b && which >= 0 && which < 5) ? b->params[which] : nullptr;
+}
+extern "C" int v2v_brain_get_iterations(const v2v_brain* b) { return b ? b->iterations : -1; }
+extern "C" int v2v_brain_set_iterations(v2v_brain* b, int t) {
+  V2V_REQUIRE(b && t >= 0, "v2v_brain_set_iterations: bad argument");
+  b->iterations = t;
+  return 0;
+}
+
+extern "C" int v2v_brain_get_params(v2v_brain* b, int which, float* host_out, void* stream) {
+  V2V_REQUIRE(b && host_out && which >= 0 && which < 5, "v2v_brain_get_params: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  V2V_CHECK_CUDA(cudaMemcpyAsync(host_out, b->params[which], b->n_params * sizeof(float), cudaMemcpyDeviceToHost, st));
+  V2V_CHECK_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int v2v_brain_set_params(v2v_brain* b, int which, const float* host_in, void* stream) {
+  V2V_REQUIRE(b && host_in && which >= 0 && which < 5, "v2v_brain_set_params: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  V2V_CHECK_CUDA(cudaMemcpyAsync(b->params[which], host_in, b->n_params * sizeof(float), cudaMemcpyHostToDevice, st));
+  V2V_CHECK_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int v2v_brain_update_target(v2v_brain* b, void* stream) {
+  V2V_REQUIRE(b, "v2v_brain_update_target: null brain");
+  V2V_CHECK_CUDA(cudaMemcpyAsync(b->params[1], b->params[0], b->n_params * sizeof(float), cudaMemcpyDeviceToDevice,
+                                 (cudaStream_t)stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// forward / backward sequencing
+// ---------------------------------------------------------------------------
+static int agg_any(v2v_brain* b, const float* H, const uint32_t* mask, const float* adj, int transpose,
+                   const float* addend, float* out, int B, void* stream) {
+  if (mask) return v2v_agg_mask(H, mask, addend, out, B, b->N, b->F, V2V_F32, stream);
+  return v2v_agg_dense(H, adj, addend, out, B, b->N, b->F, transpose, stream);
+}
+
+static int check_batch(const v2v_brain* b, int B, const char* who) {
+  V2V_REQUIRE(b, "%s: null brain", who);
+  V2V_REQUIRE(B >= 0 && B <= b->cfg.max_batch, "%s: batch %d exceeds max_batch %d", who, B, b->cfg.max_batch);
+  return 0;
+}
+
+static int forward_impl(v2v_brain* b, const float* P, const float* node, const float* edge, const float* neigh,
+                        const uint32_t* in_mask, const float* adj, int B, float* q_out, void* stream) {
+  const int N = b->N, S = b->S, G = b->G, F = b->F;
+  {
+    const float* seg[3] = {node, edge, neigh};
+    const int sw[3] = {b->Dn, b->De, F};
+    const LayerDesc& L = b->layers[0];
+    if (int rc = v2v_dense_fwd(neigh ? 3 : 2, seg, sw, P + L.w_off, L.K, P + L.b_off, b->h[0], B, N, G, F, S > 1, stream)) return rc;
+    if (int rc = agg_any(b, b->h[0], in_mask, adj, 0, nullptr, b->agg[0], B, stream)) return rc;
+  }
+  for (int s = 1; s < S; ++s) {
+    const float* seg[4] = {b->h[s - 1], node, edge, b->agg[s - 1]};
+    const int sw[4] = {F, b->Dn, b->De, F};
+    const LayerDesc& L = b->layers[s];
+    if (int rc = v2v_dense_fwd(4, seg, sw, P + L.w_off, L.K, P + L.b_off, b->h[s], B, N, G, F, s < S - 1, stream)) return rc;
+    if (int rc = agg_any(b, b->h[s], in_mask, adj, 0, nullptr, b->agg[s], B, stream)) return rc;
+  }
+  {
+    const float* seg[3] = {node, b->h[S - 1], b->agg[S - 1]};
+    const int sw[3] = {b->Dn, F, F};
+    const LayerDesc& L = b->layers[S];
+    if (int rc = v2v_dense_fwd(3, seg, sw, P + L.w_off, L.K, P + L.b_off, b->mlp[0], B, N, G, L.n_out, 1, stream)) return rc;
+  }
+  for (int j = 1; j < 4; ++j) {
+    const LayerDesc& L = b->layers[S + j];
+    const float* seg[1] = {b->mlp[j - 1]};
+    const int sw[1] = {L.K};
+    float* dst = (j == 3 && q_out) ? q_out : b->mlp[j];
+    if (int rc = v2v_dense_fwd(1, seg, sw, P + L.w_off, L.K, P + L.b_off, dst, B, N, G, L.n_out, j < 3, stream)) return rc;
+  }
+  return 0;
+}
+
+extern "C" int v2v_brain_forward(v2v_brain* b, const float* node_dev, const float* edge_dev,
+                                 const float* neighbor_dev, const uint32_t* in_mask_dev, const float* adj_dev, int B, int target,
+                                 float* q_dev, void* stream) {
+  if (int rc = check_batch(b, B, "v2v_brain_forward")) return rc;
+  if (B == 0) return 0;
+  V2V_REQUIRE(node_dev && edge_dev && q_dev, "v2v_brain_forward: null pointer");
+  V2V_REQUIRE(in_mask_dev || adj_dev, "v2v_brain_forward: need in_mask or adj");
+  return forward_impl(b, b->params[target ? 1 : 0], node_dev, edge_dev, neighbor_dev, in_mask_dev, adj_dev, B, q_dev, stream);
+}
+
+extern "C" int v2v_brain_forward_backward(v2v_brain* b, const float* node, const float* edge,
+                                          const float* neigh, const uint32_t* in_mask, const uint32_t* out_mask,
+                                          const float* adj, const float* y, int B, float* head_loss_dev,
+                                          void* stream) {
+  if (int rc = check_batch(b, B, "v2v_brain_forward_backward")) return rc;
+  V2V_REQUIRE(B > 0, "v2v_brain_forward_backward: empty batch");
+  V2V_REQUIRE(node && edge && y, "v2v_brain_forward_backward: null pointer");
+  V2V_REQUIRE((in_mask && out_mask) || adj, "v2v_brain_forward_backward: need both masks, or adj");
+  const bool use_mask = in_mask && out_mask;
+  const uint32_t* im = use_mask ? in_mask : nullptr;
+  const uint32_t* om = use_mask ? out_mask : nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = b->N, S = b->S, G = b->G, F = b->F, Dn = b->Dn, De = b->De;
+  const float* P = b->params[0];
+  float* Gd = b->params[2];
+  float* hl = head_loss_dev ? head_loss_dev : b->head_loss;
+
+  if (int rc = forward_impl(b, P, node, edge, neigh, im, adj, B, nullptr, stream)) return rc;
+  V2V_CHECK_CUDA(cudaMemsetAsync(Gd, 0, b->n_params * sizeof(float), st));
+  V2V_CHECK_CUDA(cudaMemsetAsync(hl, 0, N * sizeof(float), st));
+  if (int rc = v2v_huber_loss_grad(b->mlp[3], y, b->dq, hl, B, N, b->CH, 1.f, stream)) return rc;
+
+  // decision MLP, last layer first
+  const float* dY = b->dq;
+  for (int j = 3; j >= 1; --j) {
+    const LayerDesc& L = b->layers[S + j];
+    const float* seg[1] = {b->mlp[j - 1]};
+    const int sw[1] = {L.K};
+    if (int rc = v2v_dense_bwd_weight(1, seg, sw, dY, nullptr, Gd + L.w_off, L.K, Gd + L.b_off, B, N, G, L.n_out, stream)) return rc;
+    if (int rc = v2v_dense_bwd_data(dY, nullptr, P + L.w_off, L.K, 0, L.K, b->dmlp[j], 0, 0, nullptr, b->mlp[j - 1], B, N, G,
+                                    L.n_out, stream)) return rc;
+    dY = b->dmlp[j];
+  }
+  float* dh = b->dh_a;
+  float* dh_alt = b->dh_b;
+  {
+    const LayerDesc& L = b->layers[S];
+    const float* seg[3] = {node, b->h[S - 1], b->agg[S - 1]};
+    const int sw[3] = {Dn, F, F};
+    if (int rc = v2v_dense_bwd_weight(3, seg, sw, dY, nullptr, Gd + L.w_off, L.K, Gd + L.b_off, B, N, G, L.n_out, stream)) return rc;
+    if (int rc = v2v_dense_bwd_data(dY, nullptr, P + L.w_off, L.K, Dn, F, dh, Dn + F, F, b->dagg, nullptr, B, N, G, L.n_out,
+                                    stream)) return rc;
+    if (int rc = agg_any(b, b->dagg, om, adj, 1, dh, dh, B, stream)) return rc;
+  }
+  for (int s = S - 1; s >= 1; --s) {
+    const LayerDesc& L = b->layers[s];
+    const float* gate = (s < S - 1) ? b->h[s] : nullptr;
+    const float* seg[4] = {b->h[s - 1], node, edge, b->agg[s - 1]};
+    const int sw[4] = {F, Dn, De, F};
+    if (int rc = v2v_dense_bwd_weight(4, seg, sw, dh, gate, Gd + L.w_off, L.K, Gd + L.b_off, B, N, G, F, stream)) return rc;
+    if (int rc = v2v_dense_bwd_data(dh, gate, P + L.w_off, L.K, 0, F, dh_alt, F + Dn + De, F, b->dagg, nullptr, B, N, G, F,
+                                    stream)) return rc;
+    if (int rc = agg_any(b, b->dagg, om, adj, 1, dh_alt, dh_alt, B, stream)) return rc;
+    std::swap(dh, dh_alt);
+  }
+  {
+    const LayerDesc& L = b->layers[0];
+    const float* gate = (S > 1) ? b->h[0] : nullptr;
+    const float* seg[3] = {node, edge, neigh};
+    const int sw[3] = {Dn, De, F};
+    if (int rc = v2v_dense_bwd_weight(neigh ? 3 : 2, seg, sw, dh, gate, Gd + L.w_off, L.K, Gd + L.b_off, B, N, G, F, stream)) return rc;
+  }
+  return 0;
+}
+
+extern "C" int v2v_brain_apply_adam(v2v_brain* b, float grad_scale, void* stream) {
+  V2V_REQUIRE(b, "v2v_brain_apply_adam: null brain");
+  b->iterations += 1;
+  return v2v_adam_step(b->params[0], b->params[2], b->params[3], b->params[4], (long)b->n_params, b->iterations,
+                       b->cfg.lr, b->cfg.beta1, b->cfg.beta2, b->cfg.eps, grad_scale, stream);
+}
+
+extern "C" int v2v_brain_train_step(v2v_brain* b, const float* node, const float* edge,
+                                    const float* neigh, const uint32_t* in_mask, const uint32_t* out_mask, const float* adj,
+                                    const float* y, int B, float* head_loss_dev, void* stream) {
+  if (int rc = v2v_brain_forward_backward(b, node, edge, neigh, in_mask, out_mask, adj, y, B, head_loss_dev, stream)) return rc;
+  return v2v_brain_apply_adam(b, 1.f, stream);
+}
+
+// ---------------------------------------------------------------------------
+// host-buffer entry points (the reference-facing plugin path)
+// ---------------------------------------------------------------------------
+static int stage_inputs(v2v_brain* b, const float* node_host, const float* edge_host, const float* neigh_host,
+                        const float* adj_host,
+                        int B, bool need_out_mask, bool* weighted, cudaStream_t st) {
+  const size_t rows = (size_t)B * b->N;
+  V2V_CHECK_CUDA(cudaMemcpyAsync(b->st_node, node_host, rows * b->Dn * sizeof(float), cudaMemcpyHostToDevice, st));
+  V2V_CHECK_CUDA(cudaMemcpyAsync(b->st_edge, edge_host, rows * b->De * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (neigh_host)
+    V2V_CHECK_CUDA(cudaMemcpyAsync(b->st_neigh, neigh_host, rows * b->F * sizeof(float), cudaMemcpyHostToDevice, st));
+  V2V_CHECK_CUDA(cudaMemcpyAsync(b->st_adj, adj_host, rows * b->N * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (int rc = v2v_adj_pack_masks(b->st_adj, B, b->N, b->st_in_mask, need_out_mask ? b->st_out_mask : nullptr, b->st_flag, st))
+    return rc;
+  V2V_CHECK_CUDA(cudaMemcpyAsync(b->st_flag_host, b->st_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  V2V_CHECK_CUDA(cudaStreamSynchronize(st));
+  *weighted = (*b->st_flag_host != 0);
+  return 0;
+}
+
+extern "C" int v2v_brain_predict_host(v2v_brain* b, const float* node_host, const float* edge_host,
+                                      const float* neigh_host, const float* adj_host, int B, int target, float* q_host, void* stream) {
+  if (int rc = check_batch(b, B, "v2v_brain_predict_host")) return rc;
+  if (B == 0) return 0;
+  V2V_REQUIRE(node_host && edge_host && adj_host && q_host, "v2v_brain_predict_host: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  bool weighted = false;
+  if (int rc = stage_inputs(b, node_host, edge_host, neigh_host, adj_host, B, false, &weighted, st)) return rc;
+  if (int rc = forward_impl(b, b->params[target ? 1 : 0], b->st_node, b->st_edge, neigh_host ? b->st_neigh : nullptr,
+                            weighted ? nullptr : b->st_in_mask,
+                            b->st_adj, B, b->st_q, stream)) return rc;
+  V2V_CHECK_CUDA(cudaMemcpyAsync(q_host, b->st_q, (size_t)B * b->N * b->CH * sizeof(float), cudaMemcpyDeviceToHost, st));
+  V2V_CHECK_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int v2v_brain_train_host(v2v_brain* b, const float* node_host, const float* edge_host,
+                                    const float* neigh_host, const float* adj_host, const float* y_host, int B, float* head_loss_host,
+                                    void* stream) {
+  if (int rc = check_batch(b, B, "v2v_brain_train_host")) return rc;
+  V2V_REQUIRE(B > 0, "v2v_brain_train_host: empty batch");
+  V2V_REQUIRE(node_host && edge_host && adj_host && y_host, "v2v_brain_train_host: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  V2V_CHECK_CUDA(cudaMemcpyAsync(b->st_y, y_host, (size_t)B * b->N * b->CH * sizeof(float), cudaMemcpyHostToDevice, st));
+  bool weighted = false;
+  if (int rc = stage_inputs(b, node_host, edge_host, neigh_host, adj_host, B, true, &weighted, st)) return rc;
+  if (int rc = v2v_brain_train_step(b, b->st_node, b->st_edge, neigh_host ? b->st_neigh : nullptr,
+                                    weighted ? nullptr : b->st_in_mask,
+                                    weighted ? nullptr : b->st_out_mask, b->st_adj, b->st_y, B, b->head_loss, stream))
+    return rc;
+  if (head_loss_host)
+    V2V_CHECK_CUDA(cudaMemcpyAsync(head_loss_host, b->head_loss, b->N * sizeof(float), cudaMemcpyDeviceToHost, st));
+  V2V_CHECK_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}

@@ -1,0 +1,205 @@
+/*
+ * v2v_gnn.h -- C-ABI of the B200-native V2V graph-convolution engine.
+ *
+ * Drop-in boundary for the hot path of Coolzyh/Globecom2020-ResourceAllocationGNN:
+ * the custom Keras layers and the "brain" of BS_brain.py (reference file:line
+ * cited per entry point).  Plain `extern "C"`, raw pointers and sizes, no torch
+ * or C++ types.  The Python mirror of the reference classes
+ * (globecom2020-resourceallocationgnn_b200/{layers,brain}.py) binds these with
+ * ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; the message is
+ *     available from v2v_last_error() (thread-local).  The Python layer turns a
+ *     non-zero status into ValueError/RuntimeError like Keras would raise.
+ *   - `*_dev` pointers are device pointers, `*_host` pointers are host pointers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *     All device entry points are stream-ordered, never synchronise and never
+ *     allocate, so a step is CUDA-graph capturable.
+ *   - tensors are row-major and dense: H[B][N][F] etc.
+ *   - dtype: V2V_F32 = 0 (fp32 storage and math), V2V_BF16 = 1 (bf16 storage,
+ *     fp32 accumulate).
+ *   - adjacency is carried in compact form: one bit per directed edge,
+ *     W = ceil(N/32) 32-bit words per node, in both orientations
+ *        in_mask [b][m][w] bit n = Adj[b][n][m]   (whom m aggregates from)
+ *        out_mask[b][n][w] bit m = Adj[b][n][m]   (whom n contributes to)
+ *     Adj is the matrix of BS_brain.py:441-445 (NOT the Kronecker expansion of
+ *     :492-493; the host adapter recovers Adj from it by strided sampling).
+ */
+#ifndef V2V_GNN_H
+#define V2V_GNN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define V2V_F32 0
+#define V2V_BF16 1
+
+#define V2V_MAX_SEG 4
+
+const char* v2v_last_error(void);
+int v2v_version(void);
+/* number of SMs of the current device (grid sizing), <0 on error */
+int v2v_device_sm_count(void);
+
+/* ------------------------------------------------------------------------
+ * Adjacency packing.  Replaces the host-side np.kron of BS_brain.py:492-493,
+ * :603, :621 (dense (B,NF,NF) operand) by 2*N*W words per graph.
+ * adj_dev: fp32 [B][N][N].  nonbinary_flag_dev (int, may be NULL) is set to 1
+ * if any entry is neither 0 nor 1 (then the weighted path must be used).
+ * ---------------------------------------------------------------------- */
+int v2v_adj_pack_masks(const float* adj_dev, int B, int N,
+                       uint32_t* in_mask_dev, uint32_t* out_mask_dev,
+                       int* nonbinary_flag_dev, void* stream);
+
+/* ------------------------------------------------------------------------
+ * AggLayer.call  (BS_brain.py:69-76):
+ *     out[b][m][:] = sum_n Adj[b][n][m] * H[b][n][:]      (+ addend[b][m][:])
+ * mask_dev = in_mask for the forward; pass out_mask to get the transposed
+ * aggregation, which is the backward w.r.t. H.  addend_dev may be NULL, or may
+ * alias out_dev (accumulate).  H/out/addend are `dtype` [B][N][F].
+ * ---------------------------------------------------------------------- */
+int v2v_agg_mask(const void* H_dev, const uint32_t* mask_dev, const void* addend_dev,
+                 void* out_dev, int B, int N, int F, int dtype, void* stream);
+
+/* Weighted (non 0/1) adjacency, fp32 only: adj_dev fp32 [B][N][N];
+ * transpose = 0: out[b][m] = sum_n adj[b][n][m] H[b][n]   (forward)
+ * transpose = 1: out[b][n] = sum_m adj[b][n][m] H[b][m]   (backward) */
+int v2v_agg_dense(const float* H_dev, const float* adj_dev, const float* addend_dev,
+                  float* out_dev, int B, int N, int F, int transpose, void* stream);
+
+/* ------------------------------------------------------------------------
+ * GNNLayer.call (BS_brain.py:44-51) and Dense (:176-200) as one row-GEMM:
+ *     out[r][:] = act( [seg0[r] | seg1[r] | ...] . W[g(r)] + bias[g(r)] )
+ * rows r = b*N + n; group g(r) = n if G == N (one weight set per node slot,
+ * as the reference instantiates them, :121-142) or 0 if G == 1 (shared).
+ * W: fp32 [G][ldw][n_out], the first K = sum(seg_width) rows are used.
+ * act: 0 linear, 1 relu.   All fp32.
+ * ---------------------------------------------------------------------- */
+int v2v_dense_fwd(int n_seg, const float* const* seg_dev, const int* seg_width,
+                  const float* W_dev, int ldw, const float* bias_dev,
+                  float* out_dev, int B, int N, int G, int n_out, int act, void* stream);
+
+/* Backward w.r.t. selected input columns:
+ *     dX[r][k] = sum_o dZ[r][o] * W[g][k][o],   dZ = gate_in ? dY*(gate_in>0) : dY
+ * for k in [k0_a, k0_a+w_a) -> dxa_dev [rows][w_a] and (optional, w_b > 0)
+ * k in [k0_b, k0_b+w_b) -> dxb_dev.  gate_out_dev (optional, [rows][w_a], only
+ * when w_b == 0): dxa is zeroed where gate_out <= 0 (relu of the producer). */
+int v2v_dense_bwd_data(const float* dY_dev, const float* gate_in_dev,
+                       const float* W_dev, int ldw,
+                       int k0_a, int w_a, float* dxa_dev,
+                       int k0_b, int w_b, float* dxb_dev,
+                       const float* gate_out_dev,
+                       int B, int N, int G, int n_out, void* stream);
+
+/* Weight/bias gradient, ACCUMULATED into dW/db (zero them first):
+ *     dW[g][k][o] += sum_r x[r][k] dZ[r][o],  db[g][o] += sum_r dZ[r][o] */
+int v2v_dense_bwd_weight(int n_seg, const float* const* seg_dev, const int* seg_width,
+                         const float* dY_dev, const float* gate_in_dev,
+                         float* dW_dev, int ldw, float* db_dev,
+                         int B, int N, int G, int n_out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * huber_loss + compile(loss=huber_loss) (BS_brain.py:86-87, :214):
+ * per head k: mean over (B, CH) of huber_1(q - y); dq = clip(q-y,-1,1)/(B*CH)
+ * scaled by grad_scale.  head_loss_dev fp32 [N] is ACCUMULATED (zero it first).
+ * ---------------------------------------------------------------------- */
+int v2v_huber_loss_grad(const float* q_dev, const float* y_dev, float* dq_dev,
+                        float* head_loss_dev, int B, int N, int CH,
+                        float grad_scale, void* stream);
+
+/* DQN target rule (BS_brain.py:668-692):
+ * y = p, then y[b][k][a[b][k]] = r[b] + gamma * max_a p_next[b][k][a]. */
+int v2v_td_target(const float* p_dev, const float* p_next_dev, const int32_t* action_dev,
+                  const float* reward_dev, float gamma, float* y_dev,
+                  int B, int N, int CH, void* stream);
+
+/* keras.optimizers.Adam(lr, beta_1, beta_2) update rule of Keras 2.2.4
+ * (BS_brain.py:212), epsilon outside the sqrt; t = 1-based iteration,
+ * grad_scale multiplies g first (1/world_size after a sum all-reduce). */
+int v2v_adam_step(float* p_dev, const float* g_dev, float* m_dev, float* v_dev, long n,
+                  int t, float lr, float beta1, float beta2, float eps, float grad_scale,
+                  void* stream);
+
+/* ------------------------------------------------------------------------
+ * The brain: BS (BS_brain.py:90-239).  Owns online + target parameters, Adam
+ * state, gradients and the activation workspace for up to max_batch graphs.
+ * ---------------------------------------------------------------------- */
+typedef struct v2v_brain v2v_brain;
+
+typedef struct v2v_brain_config {
+  int num_d2d;        /* N: nodes (V2V pairs) per graph            (:95)  */
+  int node_dim;       /* Dn = ((node_info-1)*CH+1)*neighbor         (:101) */
+  int edge_dim;       /* De = edge_info*CH                          (:102) */
+  int feedback;       /* F: GNN feature width                       (:98)  */
+  int num_ch;         /* CH: Q-values per node                      (:97)  */
+  int stages;         /* GNN stages (reference: 3, :147-166)               */
+  int per_slot;       /* 1: one weight set per node slot (reference, :121-200); 0: shared */
+  int hidden[3];      /* decision MLP widths (reference 80,40,20, :176-178) */
+  int max_batch;      /* workspace capacity in graphs                      */
+  int dtype;          /* V2V_F32 (V2V_BF16: activations stored bf16)       */
+  float lr, beta1, beta2, eps;   /* Adam (:212): 1e-3, 0.5, 0.999, 1e-7    */
+} v2v_brain_config;
+
+int v2v_brain_create(const v2v_brain_config* cfg, v2v_brain** out);
+void v2v_brain_destroy(v2v_brain* b);
+/* floats in one parameter set (online == target == grads == Adam m == v) */
+long v2v_brain_param_count(const v2v_brain* b);
+/* get_weights / set_weights (BS_brain.py:239): flat fp32, per layer W[G][K][n_out] then bias[G][n_out];
+ * which = 0 online, 1 target, 2 grads, 3 adam m, 4 adam v */
+int v2v_brain_get_params(v2v_brain* b, int which, float* host_out, void* stream);
+int v2v_brain_set_params(v2v_brain* b, int which, const float* host_in, void* stream);
+float* v2v_brain_param_ptr(v2v_brain* b, int which);     /* device pointer */
+/* update_target_model (BS_brain.py:237-239) */
+int v2v_brain_update_target(v2v_brain* b, void* stream);
+int v2v_brain_get_iterations(const v2v_brain* b);
+int v2v_brain_set_iterations(v2v_brain* b, int t);
+
+/* predict (BS_brain.py:225-235): node [B][N][Dn], edge [B][N][De] fp32 device,
+ * in_mask device (binary adjacency) or adj_dev fp32 [B][N][N] (weighted; pass
+ * in_mask = NULL).  q_dev fp32 [B][N][CH].  target = 1 uses the target net.
+ * neighbor_dev: the D{k}_Neighbor_Input of the first GNN stage, fp32 [B][N][F];
+ * NULL means all zeros, which is what the reference always feeds (:478, :589) and
+ * lets the engine skip that contraction. */
+int v2v_brain_forward(v2v_brain* b, const float* node_dev, const float* edge_dev,
+                      const float* neighbor_dev,
+                      const uint32_t* in_mask_dev, const float* adj_dev,
+                      int B, int target, float* q_dev, void* stream);
+
+/* forward (online net, activations kept) + Huber + backward into the gradient
+ * buffer.  head_loss_dev fp32 [N] receives the per-head mean losses.  Does not
+ * touch the parameters: the caller may all-reduce v2v_brain_param_ptr(b, 2)
+ * across ranks before v2v_brain_apply_adam. */
+int v2v_brain_forward_backward(v2v_brain* b, const float* node_dev, const float* edge_dev,
+                               const float* neighbor_dev,
+                               const uint32_t* in_mask_dev, const uint32_t* out_mask_dev,
+                               const float* adj_dev, const float* y_dev, int B,
+                               float* head_loss_dev, void* stream);
+/* iterations += 1; Keras-Adam on the online parameters with g * grad_scale */
+int v2v_brain_apply_adam(v2v_brain* b, float grad_scale, void* stream);
+
+/* train_dnn (BS_brain.py:218-223) == one fwd+bwd+Adam step on exactly B rows. */
+int v2v_brain_train_step(v2v_brain* b, const float* node_dev, const float* edge_dev,
+                         const float* neighbor_dev,
+                         const uint32_t* in_mask_dev, const uint32_t* out_mask_dev,
+                         const float* adj_dev, const float* y_dev, int B,
+                         float* head_loss_dev, void* stream);
+
+/* Host-buffer variants: what the reference-facing plugin calls.  Inputs are
+ * host fp32 arrays (pinned for async copies), adjacency as fp32 [B][N][N];
+ * copies H2D, packs masks on device, runs, copies results D2H and waits. */
+int v2v_brain_predict_host(v2v_brain* b, const float* node_host, const float* edge_host,
+                           const float* neighbor_host /* may be NULL */,
+                           const float* adj_host, int B, int target, float* q_host, void* stream);
+int v2v_brain_train_host(v2v_brain* b, const float* node_host, const float* edge_host,
+                         const float* neighbor_host /* may be NULL */,
+                         const float* adj_host, const float* y_host, int B,
+                         float* head_loss_host, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* V2V_GNN_H */

@@ -1,0 +1,223 @@
+"""GPU parity of the brain (BS) through the reference-facing Python surface and the C-ABI host
+entry points, against the committed golden vectors and the live fp64 oracle.
+
+Tolerance: 1e-4 relative (north_star, fp32) -- measured as max|x - ref| <= 1e-4 * max|ref|.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, golden_cases
+from oracle import v2v_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+def rel_err(got, ref):
+    ref = np.asarray(ref, np.float64)
+    return float(np.abs(np.asarray(got, np.float64) - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def ref_dict(node, edge, adj, F=16, kron=True, neighbor=True):
+    """The reference's input dict (BS_brain.py:495-504): per-slot fp64 arrays + Kronecker A."""
+    B, N = node.shape[:2]
+    d = {}
+    for k in range(N):
+        d[f"D{k + 1}_Node_Input"] = node[:, k].astype(np.float64)
+        d[f"D{k + 1}_Edge_Input"] = edge[:, k].astype(np.float64)
+        if neighbor:
+            d[f"D{k + 1}_Neighbor_Input"] = np.zeros((B, F))
+    d["Adjacency_Matrix"] = np.kron(adj, np.eye(F)) if kron else adj
+    return d
+
+
+def make_brain(v2v, z, **kw):
+    N, S, per_slot = int(z["N"]), int(z["S"]), bool(z["per_slot"])
+    brain = v2v.BS(N, 3, 1, 16, 1, 4, stages=S, per_slot=per_slot, max_batch=64, data_parallel=False, **kw)
+    brain.set_flat_params(z["params"], 0)
+    brain.set_flat_params(z["target_params"], 1)
+    return brain
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_golden_predict_train(v2v, name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    brain = make_brain(v2v, z)
+    N = int(z["N"])
+    x = ref_dict(z["node"], z["edge"], z["adj"], kron=(N <= 8))
+    # --- predict: online and target nets
+    p = brain.predict(x)
+    assert isinstance(p, list) and len(p) == N and p[0].shape == (z["node"].shape[0], 4)
+    assert rel_err(np.stack(p, 1), z["q"]) <= RTOL
+    p_t = brain.predict(x, target=True)
+    assert rel_err(np.stack(p_t, 1), z["q_target"]) <= RTOL
+    # --- the agent mutates the returned arrays in place (BS_brain.py:684-690): they must be writable and independent
+    p[0][0, 0] = 123.0
+    assert p[1][0, 0] != 123.0 and brain.predict(x)[0][0, 0] != 123.0
+    # --- one fit step: loss, per-head losses and gradients
+    y = {f"D{k + 1}_Decide_Output": z["y"][:, k] for k in range(N)}
+    B = z["node"].shape[0]
+    h = brain.train_dnn(x, y, B)
+    assert abs(h.history["loss"][0] - float(z["loss"])) <= RTOL * abs(float(z["loss"]))
+    for k in range(N):
+        assert abs(h.history[f"D{k + 1}_Decide_Output_loss"][0] - z["per_head"][k]) <= RTOL * max(z["per_head"].max(), 1e-9)
+    assert rel_err(brain.get_flat_params(2), z["grads"]) <= RTOL
+    assert brain.iterations == 1
+    # --- two more Keras-Adam steps on the same batch
+    losses = [h.history["loss"][0]]
+    for _ in range(2):
+        losses.append(brain.train_dnn(x, y, B).history["loss"][0])
+    np.testing.assert_allclose(losses, z["losses_adam"], rtol=2e-4)
+    assert np.abs(brain.get_flat_params(0) - z["params_after_adam"]).max() <= 2e-5     # 3 steps of ~1e-3 each
+    # target net untouched by training, then synchronised
+    assert np.array_equal(brain.get_flat_params(1), z["target_params"])
+    brain.update_target_model()
+    assert np.array_equal(brain.get_flat_params(1), brain.get_flat_params(0))
+
+
+@pytest.mark.parametrize("N,S,per_slot,B,kind", [
+    (20, 2, False, 1024, None), (20, 3, False, 257, 2), (20, 3, True, 64, None), (4, 3, True, 512, None),
+    (4, 3, True, 1, None), (9, 1, False, 33, None), (32, 3, False, 40, None), (40, 2, False, 20, None),
+])
+def test_forward_backward_vs_live_oracle(v2v, N, S, per_slot, B, kind):
+    rng = np.random.default_rng(N * 1000 + S * 10 + B)
+    d = O.BrainDims(N, stages=S, per_slot=per_slot)
+    L = O.init_params(d, rng, bias_scale=0.05)
+    for l in L:
+        l["W"], l["b"] = l["W"].astype(np.float32).astype(np.float64), l["b"].astype(np.float32).astype(np.float64)
+    node, edge, adj, _ = O.synth_batch(B, N, rng, sparse_in_degree=kind)
+    node, edge = node.astype(np.float32), edge.astype(np.float32)
+    brain = v2v.BS(N, 3, 1, 16, 1, 4, stages=S, per_slot=per_slot, max_batch=16, data_parallel=False)
+    brain.set_flat_params(O.flatten_params(L), 0)
+    x = {"Node_Input": node, "Edge_Input": edge, "Adjacency_Matrix": adj}
+    q = np.stack(brain.predict(x), 1)
+    qr = O.brain_forward(d, L, node.astype(np.float64), edge.astype(np.float64), adj)
+    assert rel_err(q, qr) <= RTOL
+    y = (qr + rng.normal(0, 1.5, qr.shape)).astype(np.float32)
+    loss, per_head, g = O.brain_backward(d, L, node.astype(np.float64), edge.astype(np.float64), adj, y.astype(np.float64))
+    h = brain.train_dnn(x, {"Decide_Output": y}, B)
+    assert abs(h.history["loss"][0] - loss) <= RTOL * abs(loss)
+    assert rel_err(brain.get_flat_params(2), O.flatten_params(g)) <= RTOL
+
+
+def test_device_resident_path_matches_host_path(v2v):
+    rng = np.random.default_rng(77)
+    N, B = 20, 300
+    brain = v2v.BS(N, 3, 1, 16, 1, 4, stages=2, per_slot=False, max_batch=512, data_parallel=False, seed=3)
+    node, edge, adj, _ = O.synth_batch(B, N, rng)
+    node, edge, adjf = node.astype(np.float32), edge.astype(np.float32), adj.astype(np.float32)
+    q_host = np.stack(brain.predict({"Node_Input": node, "Edge_Input": edge, "Adjacency_Matrix": adjf}), 1)
+    nd, ed, ad = (torch.from_numpy(t).cuda() for t in (node, edge, adjf))
+    im, om, binary = v2v.pack_adjacency(ad)
+    assert binary
+    q_dev = brain.forward_device(nd, ed, in_mask=im).cpu().numpy()
+    assert np.array_equal(q_dev, q_host)
+    # weighted-adjacency kernels give the same answer on a 0/1 matrix
+    q_w = brain.forward_device(nd, ed, adj=ad).cpu().numpy()
+    assert rel_err(q_w, q_host) <= 1e-6
+    y = torch.from_numpy((q_host + rng.normal(0, 1, q_host.shape)).astype(np.float32)).cuda()
+    p0 = brain.get_flat_params(0)
+    l1 = brain.train_step_device(nd, ed, im, om, None, y).cpu().numpy()
+    g1 = brain.get_flat_params(2)
+    brain.set_flat_params(p0, 0)
+    l2 = brain.train_step_device(nd, ed, None, None, ad, y).cpu().numpy()
+    assert rel_err(l2, l1) <= 1e-5 and rel_err(brain.get_flat_params(2), g1) <= 1e-4
+
+
+def test_weighted_adjacency_and_neighbor_input(v2v):
+    """Non-0/1 adjacency and a non-zero D{k}_Neighbor_Input: inputs the reference's graph accepts
+    (BS_brain.py:119, :144) even though its agent never produces them."""
+    rng = np.random.default_rng(5)
+    N, B = 4, 19
+    d = O.BrainDims(N, stages=3, per_slot=True)
+    L = O.init_params(d, rng, bias_scale=0.05)
+    for l in L:
+        l["W"], l["b"] = l["W"].astype(np.float32).astype(np.float64), l["b"].astype(np.float32).astype(np.float64)
+    node, edge, _, _ = O.synth_batch(B, N, rng)
+    node, edge = node.astype(np.float32).astype(np.float64), edge.astype(np.float32).astype(np.float64)
+    adj = rng.normal(0.5, 0.5, (B, N, N)).astype(np.float32).astype(np.float64)
+    neigh = rng.normal(0, 1, (B, N, 16)).astype(np.float32).astype(np.float64)
+    brain = v2v.BS(N, 3, 1, 16, 1, 4, max_batch=32, data_parallel=False)
+    brain.set_flat_params(O.flatten_params(L), 0)
+    x = ref_dict(node, edge, adj)
+    for k in range(N):
+        x[f"D{k + 1}_Neighbor_Input"] = neigh[:, k]
+    A = np.stack([O.kron_adjacency(a, 16) for a in adj])
+    qr = np.stack(O.brain_forward_literal(d, L, node, edge, A, neigh=neigh), 1)
+    assert rel_err(np.stack(brain.predict(x), 1), qr) <= RTOL
+    y = qr + rng.normal(0, 1.0, qr.shape)
+    loss, _, g = O.brain_backward(d, L, node, edge, adj, y, neigh=neigh)
+    h = brain.train_dnn(x, [y[:, k] for k in range(N)], B)
+    assert abs(h.history["loss"][0] - loss) <= RTOL * abs(loss)
+    assert rel_err(brain.get_flat_params(2), O.flatten_params(g)) <= RTOL
+
+
+def test_bs_surface_matches_reference(v2v, tmp_path):
+    brain = v2v.BS(4, 3, 1, 16, 1, 4, data_parallel=False, seed=1)
+    # attributes the Agent reads (BS_brain.py:299, :414-417)
+    assert (brain.num_One_Node_Input, brain.num_One_Edge_Input, brain.num_One_D2D_Input, brain.num_D2D_Input,
+            brain.num_Feedback) == (9, 4, 13, 68, 16)
+    assert brain.model.count_params() == 37824
+    ws = brain.model.get_weights()
+    assert len(ws) == 4 * (3 * 4 + 4 * 2)                       # 80 weight tensors
+    assert [w.shape for w in ws[:4]] == [(9, 16), (4, 16), (16, 16), (16,)]
+    assert all(np.all(w == 0) for w in ws if w.ndim == 1)       # Keras zero biases
+    lim = np.sqrt(6.0 / (9 + 16))
+    assert np.abs(ws[0]).max() <= lim and np.abs(ws[0]).max() > 0.5 * lim      # glorot_uniform
+    # online and target nets are initialised independently (:105-106) until synchronised
+    assert not np.array_equal(ws[0], brain.target_model.get_weights()[0])
+    # save / load round trip through the target model
+    path = str(tmp_path / "w")
+    brain.model.save_weights(path)
+    brain.target_model.load_weights(path)
+    assert all(np.array_equal(a, b) for a, b in zip(brain.model.get_weights(), brain.target_model.get_weights()))
+    with pytest.raises(ValueError):
+        brain.model.set_weights(ws[:-1])
+    # Keras-style input validation
+    rng = np.random.default_rng(0)
+    node, edge, adj, _ = O.synth_batch(3, 4, rng)
+    x = ref_dict(node, edge, adj)
+    bad = dict(x); del bad["D3_Edge_Input"]
+    with pytest.raises(ValueError):
+        brain.predict(bad)
+    bad = dict(x); bad["D2_Node_Input"] = np.zeros((3, 8))
+    with pytest.raises(ValueError):
+        brain.predict(bad)
+    bad = dict(x); bad["Adjacency_Matrix"] = np.zeros((3, 60, 60))
+    with pytest.raises(ValueError):
+        brain.predict(bad)
+    with pytest.raises(ValueError):
+        brain.train_dnn(x, {"D1_Decide_Output": np.zeros((3, 4))}, 3)
+    # predict_one_step with B=1 (acting path, :336) and workspace growth beyond max_batch
+    one = ref_dict(node[:1], edge[:1], adj[:1])
+    assert brain.predict_one_step(one)[0].shape == (1, 4)
+    big_n, big_e, big_a, _ = O.synth_batch(3000, 4, rng)
+    q_big = brain.predict(ref_dict(big_n, big_e, big_a, kron=False))
+    assert q_big[0].shape == (3000, 4)
+    assert np.allclose(q_big[2][:1], brain.predict(ref_dict(big_n[:1], big_e[:1], big_a[:1]))[2], rtol=1e-5, atol=1e-6)
+
+
+def test_fit_minibatches_like_keras(v2v):
+    """rows > batch_size: ceil(rows/batch) optimiser steps in one epoch, loss = row-weighted mean."""
+    rng = np.random.default_rng(3)
+    brain = v2v.BS(4, 3, 1, 16, 1, 4, data_parallel=False, seed=2)
+    node, edge, adj, _ = O.synth_batch(10, 4, rng)
+    x = ref_dict(node, edge, adj)
+    y = [rng.normal(size=(10, 4)) for _ in range(4)]
+    h = brain.model.fit(x, y, batch_size=4, epochs=2, shuffle=False)
+    assert brain.iterations == 6 and len(h.history["loss"]) == 2
+    assert h.history["loss"][1] < h.history["loss"][0] * 1.5
+
+
+def test_training_reduces_loss(v2v):
+    rng = np.random.default_rng(4)
+    brain = v2v.BS(4, 3, 1, 16, 1, 4, data_parallel=False, seed=5)
+    node, edge, adj, _ = O.synth_batch(256, 4, rng)
+    x = ref_dict(node, edge, adj, kron=False)
+    y = [rng.normal(1.0, 0.5, (256, 4)) for _ in range(4)]
+    losses = [brain.train_dnn(x, y, 256).history["loss"][0] for _ in range(150)]
+    assert np.isfinite(losses).all() and losses[-1] < 0.5 * losses[0]

@@ -1,0 +1,67 @@
+"""Host-side logic that needs no GPU: adjacency recovery, sharding, and the data-parallel gradient
+rule (world_size 2 over gloo) checked against the full-batch oracle gradient."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import v2v_oracle as O
+
+
+def test_adjacency_from_input_shapes(v2v):
+    rng = np.random.default_rng(0)
+    adj = (rng.random((3, 4, 4)) < 0.5).astype(np.float32)
+    A = np.stack([np.kron(a, np.eye(16, dtype=np.float32)) for a in adj])
+    got = v2v.adjacency_from_input(torch.from_numpy(A), 4, 16)
+    assert torch.equal(got, torch.from_numpy(adj))
+    assert v2v.adjacency_from_input(torch.from_numpy(adj), 4, 16) is not None
+    with pytest.raises(ValueError):
+        v2v.adjacency_from_input(torch.zeros(3, 5, 5), 4, 16)
+    with pytest.raises(ValueError):
+        v2v.adjacency_from_input(torch.zeros(4, 4), 4, 16)
+
+
+def test_shard_range_partitions_batch(v2v):
+    from importlib import import_module
+    par = import_module("globecom2020-resourceallocationgnn_b200.parallel")
+    for B, W in [(8192, 8), (1000, 8), (7, 2), (3, 4)]:
+        spans = [par.shard_range(B, r, W) for r in range(W)]
+        assert spans[0][0] == 0 and spans[-1][1] == B
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(W - 1))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _dp_worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from importlib import import_module
+    par = import_module("globecom2020-resourceallocationgnn_b200.parallel")
+    rng = np.random.default_rng(11)
+    d = O.BrainDims(num_d2d=6, stages=2, per_slot=False)
+    L = O.init_params(d, rng, bias_scale=0.1)
+    B = 10
+    node, edge, adj, _ = O.synth_batch(B, 6, rng)
+    y = O.brain_forward(d, L, node, edge, adj) + rng.normal(0, 1.5, (B, 6, 4))
+    lo, hi = par.shard_range(B, rank, world)
+    _, ph, g = O.brain_backward(d, L, node[lo:hi], edge[lo:hi], adj[lo:hi], y[lo:hi])
+    flat = torch.from_numpy(np.concatenate([O.flatten_params(g), ph]))
+    # the engine's rule: SUM all-reduce of [grads | head losses], then scale by the shard weights
+    par.allreduce_gradients_(flat, weight=(hi - lo) / (B / world))
+    flat /= world
+    _, ph_full, g_full = O.brain_backward(d, L, node, edge, adj, y)
+    ref = np.concatenate([O.flatten_params(g_full), ph_full])
+    err = np.abs(flat.numpy() - ref).max()
+    np.save(os.path.join(tmp, f"err{rank}.npy"), np.array(err))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_rule_gloo_world2(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_dp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert float(np.load(tmp_path / f"err{r}.npy")) < 1e-12
