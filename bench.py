@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""Benchmark of the V2V graph-convolution hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's sm_100a engine
+    python bench.py --impl reference [--gpus N] --steps K --warmup W   # the reference's CPU form
+
+One "step" = one fwd + Huber + bwd + Keras-Adam pass of the brain (BS.train_dnn, BS_brain.py:218-223)
+over one batch of synthetic V2V graphs.  Workload at every N: BASELINE.json configs[1] per GPU --
+batch 1024 x 20-vehicle graphs, 2 GNN stages, fp32 -- i.e. weak scaling (1024 graphs per GPU; 8 GPUs
+= the 8192-graph configs[2] shape).  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PKG = "globecom2020-resourceallocationgnn_b200"
+L2_BYTES = 126 * 1024 * 1024
+SEED = 1001                      # the reference's training seed (RL_Train_main.py:44)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="graphs per GPU")
+    ap.add_argument("--nodes", type=int, default=20)
+    ap.add_argument("--stages", type=int, default=2)
+    ap.add_argument("--per-slot", type=int, default=0)
+    ap.add_argument("--sparse", type=int, default=0, help="in-degree of the sparse variant (0 = reference-dense E=N(N-2))")
+    ap.add_argument("--agg-batch", type=int, default=8192, help="graphs of the aggregation roofline point")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    E = a.nodes * (a.sparse if a.sparse else a.nodes - 2)
+    return (f"BASELINE configs[1]: batch {a.batch} x {a.nodes}-vehicle graphs per GPU, E={E} directed edges/graph "
+            f"({'sparse' if a.sparse else 'reference-dense'}), {a.stages}-stage GNN (last stage linear) + 80-40-20-4 MLP, "
+            f"{'per-slot' if a.per_slot else 'shared'} weights, fwd+Huber+bwd+Keras-Adam, fp32")
+
+
+# --------------------------------------------------------------------------- synthetic data
+def synth_numpy(B, N, rng, sparse=0, CH=4):
+    """Feature distributions measured on the reference simulator."""
+    v2v = rng.normal(0.66, 0.44, (B, N, CH))
+    v2i = rng.normal(0.54, 0.17, (B, N, CH))
+    node = np.concatenate([v2v, v2i, np.full((B, N, 1), 10.0)], -1).astype(np.float32)
+    edge = rng.normal(0.92, 0.11, (B, N, CH)).astype(np.float32)
+    cols = np.tile(np.arange(N), B)
+    rows_b = np.repeat(np.arange(B), N)
+    if not sparse:
+        dest = (np.arange(N)[None, :] + rng.integers(1, N, (B, N))) % N       # BS_brain.py:441-445
+        adj = np.ones((B, N, N), np.float32) - np.eye(N, dtype=np.float32)[None]
+        adj[rows_b, dest.ravel(), cols] = 0.0
+    else:
+        adj = np.zeros((B, N, N), np.float32)
+        r = rng.integers(0, N - 1, (B, N))
+        for k in range(sparse):
+            src = (np.arange(N)[None, :] + 1 + (r + k) % (N - 1)) % N
+            adj[rows_b, src.ravel(), cols] = 1.0
+    return node, edge, adj
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:                                      # pragma: no cover
+            self.nv, self.err = None, repr(e)
+
+    def _run(self):
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv:
+            self._stop.clear()
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *exc):
+        if self._t:
+            self._stop.set()
+            self._t.join()
+            self._t = None
+
+    def summary(self):
+        if not self.nv or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_run(a, steps, warmup, budget_s, note):
+    """The reference's own CPU form (oracle/torch_ref.py: per-slot layer calls, (B,NF)x(B,NF,NF) bmm
+    against the dense Kronecker adjacency, autograd, Keras-Adam) on all host cores."""
+    import torch
+    from oracle import v2v_oracle as O
+    from oracle import torch_ref as T
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rng = np.random.default_rng(SEED)
+    d = O.BrainDims(a.nodes, stages=a.stages, per_slot=bool(a.per_slot))
+    layers = O.init_params(d, rng)
+
+    def make(bs):
+        node, edge, adj = synth_numpy(bs, a.nodes, rng, a.sparse)
+        A = np.kron(adj, np.eye(d.F, dtype=np.float32))                      # BS_brain.py:603
+        y = rng.normal(0, 1, (bs, a.nodes, d.CH)).astype(np.float32)
+        return [torch.from_numpy(t) for t in (node, edge, A, y)]
+
+    model = T.ReferenceFormCPU(d, layers, dtype=torch.float32, form="reference")
+    # size the per-step sample so that the whole run fits the budget
+    probe = make(32)
+    model.fit_step(*probe)
+    t0 = time.perf_counter(); model.fit_step(*probe); t_probe = time.perf_counter() - t0
+    per_graph = t_probe / 32
+    bs = a.batch
+    if steps is None:                     # time-boxed: as many full batches as fit the budget
+        steps = int(max(5, min(200, budget_s / max(per_graph * bs, 1e-6))))
+    while bs > 16 and per_graph * bs * (steps + warmup) > 1.5 * budget_s:
+        bs //= 2
+    data = make(bs)
+    for _ in range(warmup):
+        model.fit_step(*data)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter(); model.fit_step(*data); times.append(time.perf_counter() - t0)
+    total = float(np.sum(times))
+    val = bs * steps / total
+    sample = (f"{steps} steps (+{warmup} warm-up) of {bs} graphs each (of the {a.batch}-graph batch), reference-form "
+              f"fwd+bwd+Keras-Adam, torch-CPU fp32, {note}")
+    return {"value": val, "unit": "graphs/s", "cores": int(torch.get_num_threads()), "kind": "port", "sample": sample,
+            "ms_per_step": 1e3 * total / steps, "median_ms_per_step": 1e3 * float(np.median(times)), "graphs_per_step": bs}
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_reference_run(a, a.steps, a.warmup, budget_s=150.0,
+                            note="oracle port (TF1/Keras cannot run in this image: BASELINE.md section 2)")
+    line = {
+        "impl": "reference", "metric": "V2V graphs/sec (fwd+bwd)", "value": res["value"], "unit": "graphs/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": res["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "device": "host CPU"},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- the engine arm
+def run_engine_arm(a):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    v2v = importlib.import_module(PKG)
+    lib = v2v.load_library()
+    ptr = v2v._lib.ptr
+    N, B, S, CH = a.nodes, a.batch, a.stages, 4
+    brain = v2v.BS(N, 3, 1, 16, 1, CH, stages=S, per_slot=bool(a.per_slot), max_batch=max(B, 1), data_parallel=(world > 1),
+                   seed=SEED)
+    brain.update_target_model()
+    if world > 1:                                              # identical replicas
+        for w in (0, 1):
+            dist.broadcast(brain._views[w], src=0)
+
+    # ---- rotating pool of device-resident batches, larger than L2 in total
+    rng = np.random.default_rng(SEED + rank)
+    per_batch = B * N * (9 + 4 + 4) * 4 + 2 * B * N * 4
+    R = max(4, -(-int(1.15 * L2_BYTES) // per_batch))
+    pool = []
+    st = v2v._lib.current_stream
+    for i in range(R):
+        node, edge, adj = synth_numpy(B, N, rng, a.sparse)
+        nd, ed, ad = (torch.from_numpy(t).to(dev) for t in (node, edge, adj))
+        im, om, binary = v2v.pack_adjacency(ad)
+        assert binary
+        p = brain.forward_device(nd, ed, in_mask=im)
+        pn = brain.forward_device(nd, ed, in_mask=im, target=True)
+        act = torch.from_numpy(rng.integers(0, CH, (B, N)).astype(np.int32)).to(dev)
+        rew = torch.from_numpy(rng.normal(10.0, 3.0, B).astype(np.float32)).to(dev)
+        y = torch.empty_like(p)
+        v2v._lib.check(lib.v2v_td_target(ptr(p), ptr(pn), ptr(act), ptr(rew), 0.5, ptr(y), B, N, CH, st()))   # :668-692
+        pool.append((nd, ed, im, om, y))
+        del ad
+    head_loss = torch.zeros(N, device=dev)
+    torch.cuda.synchronize()
+
+    def step(i):
+        nd, ed, im, om, y = pool[i % R]
+        brain.train_step_device(nd, ed, im, om, None, y, head_loss=head_loss)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(a.warmup, 3)):
+        step(i)
+    barrier()
+    clocks = ClockSampler(local)
+    launches0 = lib.v2v_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with clocks:
+        barrier()
+        e0.record()
+        for i in range(a.steps):
+            step(a.warmup + i)
+        e1.record()
+        barrier()
+    launches = lib.v2v_launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * B * a.steps / (ms_total * 1e-3)
+    loss_now = float(head_loss.sum().item())
+    assert np.isfinite(loss_now), "non-finite loss in the timed region"
+
+    # ---- e2e: the reference-facing call with HOST buffers (BS.train_dnn), copies inside the timed region
+    e2e = None
+    if not a.no_e2e:
+        host = []
+        for i in range(8):
+            node, edge, adj = synth_numpy(B, N, rng, a.sparse)
+            yh = rng.normal(0, 1, (B, N, CH)).astype(np.float32)
+            host.append(({"Node_Input": node, "Edge_Input": edge, "Adjacency_Matrix": adj}, {"Decide_Output": yh}))
+        for i in range(3):
+            brain.train_dnn(host[i % 8][0], host[i % 8][1], B)
+        k_e2e = max(20, min(a.steps, 200))
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(k_e2e):
+            brain.train_dnn(host[i % 8][0], host[i % 8][1], B)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        h2d = B * N * (9 + 4 + N + CH) * 4
+        d2h = N * 4 + 4
+        e2e = {"value": world * B * k_e2e / float(dt.item()), "unit": "graphs/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": k_e2e,
+               "api": "BS.train_dnn(x_dict, y_dict, B) -> v2v_brain_train_host (numpy fp32 in, pinned staging, H2D, "
+                      "mask packing, fwd+bwd+Adam, D2H of the per-head losses)"}
+
+    # ---- roofline of the neighbour-aggregation kernel at the north-star point
+    roof = None
+    if rank == 0:
+        roof = agg_roofline(v2v, lib, dev, a.agg_batch, N, a.sparse, clocks)
+    cpu = None
+    if rank == 0 and not a.no_cpu_baseline:
+        cpu = cpu_baseline_bounded(a)
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        peaks = load_peaks()
+        line = {
+            "metric": "V2V graphs/sec (fwd+bwd)", "value": value, "unit": "graphs/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "global_batch": world * B, "graphs_per_gpu": B, "nodes": N, "stages": S,
+                       "parallelism": f"dp{world}" if world > 1 else "single",
+                       "collective": "one NCCL sum all-reduce of the flat fp32 gradient per step" if world > 1 else "none",
+                       "l2": f"rotating pool of {R} distinct device-resident input batches ({R * per_batch / 2**20:.0f} MiB "
+                             f"> 126 MiB L2); roofline loop rotates over buffer sets > L2 as well",
+                       "final_loss": loss_now},
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu, "peaks": peaks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "source": "MEASURED_PEAKS.json (measured)"}
+    return {"hbm_gbs": 6650.0, "source": "B200_PROFILING.md fallback"}
+
+
+def agg_roofline(v2v, lib, dev, B, N, sparse, clocks):
+    """Average launch duration of the aggregation kernel at (B, N, F=16, fp32), cold L2: a CUDA graph of P
+    launches over P distinct (H, mask, out) sets whose total exceeds L2, replayed between two events."""
+    import torch
+    F = 16
+    rng = np.random.default_rng(SEED)
+    bytes_per_graph = 2 * N * F * 4 + N * ((N + 31) // 32) * 4          # read H + write agg + in_mask bits
+    set_bytes = B * bytes_per_graph
+    P = max(8, -(-2 * L2_BYTES // set_bytes))
+    sets = []
+    _, _, adj = synth_numpy(min(B, 2048), N, rng, sparse)
+    adj = np.tile(adj, (-(-B // adj.shape[0]), 1, 1))[:B]
+    im0, _, _ = v2v.pack_adjacency(torch.from_numpy(adj).to(dev))
+    for i in range(P):
+        H = torch.randn((B, N, F), device=dev)
+        sets.append((H, im0.clone(), torch.empty_like(H)))
+    ptr = v2v._lib.ptr
+
+    def launch(i):
+        H, im, out = sets[i]
+        v2v._lib.check(lib.v2v_agg_mask(ptr(H), ptr(im), None, ptr(out), B, N, F, 0, v2v._lib.current_stream()))
+
+    for i in range(P):
+        launch(i)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(P):
+            launch(i)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    reps = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with clocks:
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+    us = 1e3 * e0.elapsed_time(e1) / (reps * P)
+    peaks = load_peaks()
+    achieved = set_bytes / (us * 1e-6) / 1e9
+    return {"bound": "hbm", "kernel": "agg_mask_f16_kernel (neighbour aggregation, AggLayer.call)",
+            "point": f"B={B} graphs x N={N} nodes x F=16, fp32, E={N * (sparse if sparse else N - 2)} edges/graph",
+            "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+            "peak_source": peaks["source"], "algorithmic_bytes_per_launch": set_bytes, "bytes_per_graph": bytes_per_graph,
+            "avg_launch_us": us, "launches_timed": reps * P,
+            "method": f"CUDA graph of {P} back-to-back launches over {P} distinct buffer sets ({P * set_bytes / 2**20:.0f} MiB "
+                      f"> L2), {reps} replays between two CUDA events on the launch stream",
+            "traffic": None}
+
+
+def cpu_baseline_bounded(a):
+    """~10-30 s of host work: the reference-form step on a bounded sample of the same workload."""
+    return {k: v for k, v in cpu_reference_run(a, None, 3, budget_s=12.0,
+                                               note="oracle port timed on the GPU box's host cores").items()
+            if k in ("value", "unit", "cores", "kind", "sample")}
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_engine_arm(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -35,6 +35,7 @@ SIGNATURES = {
     "v2v_last_error": (C.c_char_p, []),
     "v2v_version": (C.c_int, []),
     "v2v_device_sm_count": (C.c_int, []),
+    "v2v_launch_count": (C.c_long, []),
     "v2v_adj_pack_masks": (C.c_int, [c_void_p, C.c_int, C.c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "v2v_agg_mask": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
     "v2v_agg_dense": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),

@@ -30,6 +30,11 @@ int fail(const char* fmt, ...) {
   return 1;
 }
 
+long& launch_counter() {
+  static long n = 0;
+  return n;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -83,6 +88,7 @@ static int dmalloc(float** p, size_t n_floats) {
 extern "C" const char* v2v_last_error(void) { return last_error().c_str(); }
 extern "C" int v2v_version(void) { return 100; }
 extern "C" int v2v_device_sm_count(void) { return sm_count(); }
+extern "C" long v2v_launch_count(void) { return launch_counter(); }
 
 extern "C" void v2v_brain_destroy(v2v_brain* b) {
   if (!b) return;

@@ -27,7 +27,10 @@ int fail(const char* fmt, ...);
     if (!(cond)) return ::v2v::fail(__VA_ARGS__); \
   } while (0)
 
+long& launch_counter();   // kernels launched by this library in this process (bench evidence)
+
 inline int launch_status(const char* what) {
+  ++launch_counter();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail("%s launch failed: %s", what, cudaGetErrorString(e));
   return 0;

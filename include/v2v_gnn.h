@@ -44,6 +44,8 @@ const char* v2v_last_error(void);
 int v2v_version(void);
 /* number of SMs of the current device (grid sizing), <0 on error */
 int v2v_device_sm_count(void);
+/* kernels this library has launched in this process so far (bench.py's gpu_launches) */
+long v2v_launch_count(void);
 
 /* ------------------------------------------------------------------------
  * Adjacency packing.  Replaces the host-side np.kron of BS_brain.py:492-493,

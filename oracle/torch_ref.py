@@ -119,6 +119,8 @@ def huber_total(q_list_or_tensor, y):
 
 def keras_adam_(params, grads, ms, vs, t, lr=1e-3, beta1=0.5, beta2=0.999, eps=1e-7):
     """In-place Keras-2.2.4 Adam over lists of tensors (BS_brain.py:212)."""
+    import numpy as _np
+    lr, beta1, beta2, eps = (float(_np.float32(x)) for x in (lr, beta1, beta2, eps))   # Keras float32 variables
     lr_t = lr * ((1.0 - beta2 ** t) ** 0.5 / (1.0 - beta1 ** t))
     with torch.no_grad():
         for p, g, m, v in zip(params, grads, ms, vs):

@@ -315,15 +315,20 @@ def brain_loss(q, y):
     return per_head.sum(), per_head
 
 
-def brain_backward(dims: BrainDims, layers, node, edge, adj, y, neigh=None):
+def brain_backward(dims: BrainDims, layers, node, edge, adj, y, neigh=None, q_for_loss=None):
     """Manual reverse pass of brain_forward + brain_loss.
 
     Returns (loss, per_head, grads) with grads in the same structure as layers.
+    ``q_for_loss`` (optional) replaces the network output inside the Huber residual q - y only:
+    tests use it to feed the fp32-rounded output of the device, which separates the parity of the
+    backward kernels from the cancellation in q - y when |q| >> |q - y|.
     """
     S = dims.S
     F, Dn, De = dims.F, dims.Dn, dims.De
     q, tape = brain_forward(dims, layers, node, edge, adj, keep=True, neigh=neigh)
     B = q.shape[0]
+    if q_for_loss is not None:
+        q = np.asarray(q_for_loss, dtype=q.dtype)
     loss, per_head = brain_loss(q, y)
     grads = [{'W': np.zeros_like(l['W']), 'b': np.zeros_like(l['b'])} for l in layers]
 
@@ -368,7 +373,14 @@ def brain_backward(dims: BrainDims, layers, node, edge, adj, y, neigh=None):
 
 
 def keras_adam_step(p, g, m, v, t, lr=1e-3, beta1=0.5, beta2=0.999, eps=1e-7):
-    """One update; ``t`` is the 1-based iteration.  Returns (p, m, v)."""
+    """One update; ``t`` is the 1-based iteration.  Returns (p, m, v).
+
+    Keras keeps lr / beta_1 / beta_2 as float32 ``K.variable``s and evaluates the rule in
+    float32, so the hyper-parameters are rounded to fp32 first (0.999 -> 0.99900001287...,
+    which changes 1 - beta_2 by 1.3e-5 relative); the arithmetic itself stays in the dtype of
+    the arrays passed in (fp64 for the high-precision oracle).
+    """
+    lr, beta1, beta2, eps = (float(np.float32(x)) for x in (lr, beta1, beta2, eps))
     lr_t = lr * (np.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t))
     m = beta1 * m + (1.0 - beta1) * g
     v = beta2 * v + (1.0 - beta2) * g * g

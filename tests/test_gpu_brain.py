@@ -35,6 +35,23 @@ def ref_dict(node, edge, adj, F=16, kron=True, neighbor=True):
     return d
 
 
+def check_grads(g_gpu, z, q_gpu, neigh=None):
+    """Backward parity.  The Huber residual q - y cancels catastrophically when |q| >> |q - y|
+    (untrained nets at N=20 output |q| ~ 1e3 against residuals ~ 1): ANY fp32 forward, the
+    reference's TF1 graph included, then carries ~eps*|q| absolute error into dq.  So (1) the
+    backward kernels are checked at 1e-4 against the fp64 oracle fed with the device's own
+    fp32 output inside the residual, and (2) the whole chain against the pure-fp64 gradient with
+    that measured sensitivity added to the tolerance."""
+    d = O.BrainDims(int(z["N"]), stages=int(z["S"]), per_slot=bool(z["per_slot"]))
+    L = O.unflatten_params(d, np.asarray(z["params"], np.float64))
+    args = [np.asarray(z[k], np.float64) for k in ("node", "edge", "adj", "y")]
+    _, _, g_cond = O.brain_backward(d, L, *args, neigh=neigh, q_for_loss=q_gpu)
+    g_cond = O.flatten_params(g_cond)
+    assert rel_err(g_gpu, g_cond) <= RTOL
+    sens = rel_err(g_cond, z["grads"])
+    assert rel_err(g_gpu, z["grads"]) <= RTOL + 2 * sens
+
+
 def make_brain(v2v, z, **kw):
     N, S, per_slot = int(z["N"]), int(z["S"]), bool(z["per_slot"])
     brain = v2v.BS(N, 3, 1, 16, 1, 4, stages=S, per_slot=per_slot, max_batch=64, data_parallel=False, **kw)
@@ -52,7 +69,8 @@ def test_golden_predict_train(v2v, name):
     # --- predict: online and target nets
     p = brain.predict(x)
     assert isinstance(p, list) and len(p) == N and p[0].shape == (z["node"].shape[0], 4)
-    assert rel_err(np.stack(p, 1), z["q"]) <= RTOL
+    q_gpu = np.stack(p, 1).astype(np.float64)
+    assert rel_err(q_gpu, z["q"]) <= RTOL
     p_t = brain.predict(x, target=True)
     assert rel_err(np.stack(p_t, 1), z["q_target"]) <= RTOL
     # --- the agent mutates the returned arrays in place (BS_brain.py:684-690): they must be writable and independent
@@ -65,14 +83,31 @@ def test_golden_predict_train(v2v, name):
     assert abs(h.history["loss"][0] - float(z["loss"])) <= RTOL * abs(float(z["loss"]))
     for k in range(N):
         assert abs(h.history[f"D{k + 1}_Decide_Output_loss"][0] - z["per_head"][k]) <= RTOL * max(z["per_head"].max(), 1e-9)
-    assert rel_err(brain.get_flat_params(2), z["grads"]) <= RTOL
+    check_grads(brain.get_flat_params(2), z, q_gpu)
     assert brain.iterations == 1
-    # --- two more Keras-Adam steps on the same batch
-    losses = [h.history["loss"][0]]
-    for _ in range(2):
-        losses.append(brain.train_dnn(x, y, B).history["loss"][0])
-    np.testing.assert_allclose(losses, z["losses_adam"], rtol=2e-4)
-    assert np.abs(brain.get_flat_params(0) - z["params_after_adam"]).max() <= 2e-5     # 3 steps of ~1e-3 each
+    # --- Keras-Adam.  The rule is m/(sqrt(v)+1e-7): for the handful of weights whose gradient is
+    # ~1e-7 the update is as ill-conditioned as the fp32 gradient itself, so the optimiser kernel is
+    # checked exactly (fp64 rule applied to the device's own gradients), the loss of every step
+    # against the oracle evaluated at the device's parameters, and the committed fp64 trajectory in
+    # bulk (Adam normalises each weight's step to ~lr whatever its gradient's size, so weights with
+    # |g| << max|g| amplify the fp32 rounding of g: mean drift <= 1e-4, none beyond three full steps).
+    d = O.BrainDims(N, stages=int(z["S"]), per_slot=bool(z["per_slot"]))
+    arrs = [np.asarray(z[k], np.float64) for k in ("node", "edge", "adj", "y")]
+    p_ref = z["params"].astype(np.float64)
+    m_ref, v_ref = np.zeros_like(p_ref), np.zeros_like(p_ref)
+    p_ref, m_ref, v_ref = O.keras_adam_step(p_ref, brain.get_flat_params(2).astype(np.float64), m_ref, v_ref, 1)
+    assert np.abs(brain.get_flat_params(0) - p_ref).max() <= 1e-6
+    for t in (2, 3):
+        p_now = brain.get_flat_params(0).astype(np.float64)
+        loss_ref, _, _ = O.brain_backward(d, O.unflatten_params(d, p_now), *arrs)
+        loss_t = brain.train_dnn(x, y, B).history["loss"][0]
+        assert abs(loss_t - loss_ref) <= RTOL * abs(loss_ref)
+        p_ref, m_ref, v_ref = O.keras_adam_step(p_now, brain.get_flat_params(2).astype(np.float64), m_ref, v_ref, t)
+        assert np.abs(brain.get_flat_params(0) - p_ref).max() <= 1e-6
+        assert np.abs(brain.get_flat_params(3) - m_ref).max() <= 1e-6 * max(1.0, np.abs(m_ref).max())
+    assert brain.iterations == 3
+    diff = np.abs(brain.get_flat_params(0) - z["params_after_adam"])
+    assert diff.mean() <= 1e-4 and diff.max() <= 3.2e-3
     # target net untouched by training, then synchronised
     assert np.array_equal(brain.get_flat_params(1), z["target_params"])
     brain.update_target_model()
@@ -101,7 +136,9 @@ def test_forward_backward_vs_live_oracle(v2v, N, S, per_slot, B, kind):
     loss, per_head, g = O.brain_backward(d, L, node.astype(np.float64), edge.astype(np.float64), adj, y.astype(np.float64))
     h = brain.train_dnn(x, {"Decide_Output": y}, B)
     assert abs(h.history["loss"][0] - loss) <= RTOL * abs(loss)
-    assert rel_err(brain.get_flat_params(2), O.flatten_params(g)) <= RTOL
+    z = {"N": N, "S": S, "per_slot": per_slot, "params": O.flatten_params(L), "node": node, "edge": edge, "adj": adj,
+         "y": y, "grads": O.flatten_params(g)}
+    check_grads(brain.get_flat_params(2), z, q.astype(np.float64))
 
 
 def test_device_resident_path_matches_host_path(v2v):
@@ -151,9 +188,12 @@ def test_weighted_adjacency_and_neighbor_input(v2v):
     assert rel_err(np.stack(brain.predict(x), 1), qr) <= RTOL
     y = qr + rng.normal(0, 1.0, qr.shape)
     loss, _, g = O.brain_backward(d, L, node, edge, adj, y, neigh=neigh)
+    q_gpu = np.stack(brain.predict(x), 1).astype(np.float64)
     h = brain.train_dnn(x, [y[:, k] for k in range(N)], B)
     assert abs(h.history["loss"][0] - loss) <= RTOL * abs(loss)
-    assert rel_err(brain.get_flat_params(2), O.flatten_params(g)) <= RTOL
+    z = {"N": N, "S": 3, "per_slot": True, "params": O.flatten_params(L), "node": node, "edge": edge, "adj": adj,
+         "y": y, "grads": O.flatten_params(g)}
+    check_grads(brain.get_flat_params(2), z, q_gpu, neigh=neigh)
 
 
 def test_bs_surface_matches_reference(v2v, tmp_path):

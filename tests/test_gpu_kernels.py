@@ -149,7 +149,8 @@ def test_agg_empty_batch_and_errors(v2v):
     H = torch.zeros((2, 4, 16), device="cuda")
     m = torch.zeros((2, 4, 1), dtype=torch.int32, device="cuda")
     assert lib.v2v_agg_mask(H.data_ptr(), m.data_ptr(), None, H.data_ptr(), 2, 4, 16, 0, None) != 0   # out aliases H
-    assert lib.v2v_agg_mask(H.data_ptr(), m.data_ptr(), None, H.data_ptr(), 2, 4, 16, 7, None) != 0
+    o = torch.zeros_like(H)
+    assert lib.v2v_agg_mask(H.data_ptr(), m.data_ptr(), None, o.data_ptr(), 2, 4, 16, 7, None) != 0
 
 
 # --------------------------------------------------------------------------- dense layers
