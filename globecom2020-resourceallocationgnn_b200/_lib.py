@@ -38,6 +38,8 @@ SIGNATURES = {
     "v2v_launch_count": (C.c_long, []),
     "v2v_adj_pack_masks": (C.c_int, [c_void_p, C.c_int, C.c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "v2v_agg_mask": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
+    "v2v_agg_mask_ex": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint,
+                                  c_void_p]),
     "v2v_agg_dense": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
     "v2v_dense_fwd": (C.c_int, [C.c_int, C.POINTER(c_void_p), C.POINTER(C.c_int), c_void_p, C.c_int, c_void_p,
                                 c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),

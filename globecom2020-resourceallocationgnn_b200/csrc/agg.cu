@@ -18,174 +18,9 @@
 //     LDS.128 each) and adds the row into the accumulators whose mask bit is set
 //     (predicated packed FADD2), i.e. a register-tiled gather-reduce.
 // Generic path: any N <= 256 / F, one thread per output element.
-#include "v2v_common.cuh"
+#include "agg_kernels.cuh"
 
 namespace v2v {
-
-// ---------------------------------------------------------------------------
-// fast path
-// ---------------------------------------------------------------------------
-constexpr int kAggWarps = 8;        // warps per CTA
-constexpr int kAggStages = 2;       // smem ring depth per warp
-
-struct AggTileSizes {
-  int h_bytes;       // TG * N * 16 * sizeof(T)
-  int mask_bytes;    // TG * N * 4
-  int stage_bytes;   // h + mask (+ addend), 128-B aligned
-  int out_bytes;     // == h_bytes
-  int warp_bytes;    // stages * stage + out
-};
-
-template <typename T>
-__host__ __device__ inline AggTileSizes agg_tile_sizes(int N, int TG, bool has_addend) {
-  AggTileSizes s;
-  s.h_bytes = TG * N * 16 * (int)sizeof(T);
-  s.mask_bytes = TG * N * 4;
-  int st = s.h_bytes + (has_addend ? s.h_bytes : 0) + s.mask_bytes;
-  s.stage_bytes = (st + 127) & ~127;
-  s.out_bytes = (s.h_bytes + 127) & ~127;
-  s.warp_bytes = kAggStages * s.stage_bytes + s.out_bytes;
-  return s;
-}
-
-__device__ __forceinline__ float4 ld_row4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ float4 ld_row4(const __nv_bfloat16* p) {
-  uint2 u = *reinterpret_cast<const uint2*>(p);
-  float4 r;
-  r.x = __uint_as_float(u.x << 16);
-  r.y = __uint_as_float(u.x & 0xffff0000u);
-  r.z = __uint_as_float(u.y << 16);
-  r.w = __uint_as_float(u.y & 0xffff0000u);
-  return r;
-}
-__device__ __forceinline__ void st_row4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ void st_row4(__nv_bfloat16* p, float4 v) {
-  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
-  __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
-  uint2 u;
-  u.x = *reinterpret_cast<uint32_t*>(&a);
-  u.y = *reinterpret_cast<uint32_t*>(&b);
-  *reinterpret_cast<uint2*>(p) = u;
-}
-
-__device__ __forceinline__ void add4(float4& a, const float4& v) {
-  float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(v.x, v.y));
-  float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(v.z, v.w));
-  a.x = lo.x; a.y = lo.y; a.z = hi.x; a.w = hi.y;
-}
-
-// T: storage type. MT: targets per lane. MP: target partitions (lanes per graph = 4*MP).
-template <typename T, int MT, int MP, bool ADD>
-__global__ void __launch_bounds__(kAggWarps * 32, 1)
-agg_mask_f16_kernel(const T* __restrict__ H, const uint32_t* __restrict__ mask,
-                    const T* __restrict__ addend, T* __restrict__ out, int B, int N) {
-  constexpr int TG = 32 / (4 * MP);           // graphs per warp tile
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[kAggWarps][kAggStages];
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = lane & 3, mp = (lane >> 2) % MP, gl = lane / (4 * MP);
-  const AggTileSizes ts = agg_tile_sizes<T>(N, TG, ADD);
-  uint8_t* wbase = smem_raw + (size_t)warp * ts.warp_bytes;
-  uint8_t* out_s = wbase + kAggStages * ts.stage_bytes;
-
-  const int num_tiles = (B + TG - 1) / TG;
-  const int warp_stride = gridDim.x * kAggWarps;
-  int tile = blockIdx.x * kAggWarps + warp;
-
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < kAggStages; ++s) mbar_init(&bars[warp][s], 1);
-    fence_mbar_init();
-  }
-  __syncwarp();
-
-  const size_t graph_elems = (size_t)N * 16;
-
-  auto issue = [&](int t, int s) {     // lane 0 only
-    int ng = min(TG, B - t * TG);
-    uint32_t hb = (uint32_t)(ng * N * 16 * sizeof(T));
-    uint32_t mb = (uint32_t)(ng * N * 4);
-    bool mask_bulk = (mb & 15u) == 0;
-    uint8_t* st = wbase + s * ts.stage_bytes;
-    uint32_t tx = hb + (ADD ? hb : 0) + (mask_bulk ? mb : 0);
-    mbar_arrive_expect_tx(&bars[warp][s], tx);
-    bulk_g2s(st, H + (size_t)t * TG * graph_elems, hb, &bars[warp][s]);
-    if (ADD) bulk_g2s(st + ts.h_bytes, addend + (size_t)t * TG * graph_elems, hb, &bars[warp][s]);
-    if (mask_bulk)
-      bulk_g2s(st + ts.h_bytes * (ADD ? 2 : 1), mask + (size_t)t * TG * N, mb, &bars[warp][s]);
-  };
-
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < kAggStages; ++s) {
-      int t = tile + s * warp_stride;
-      if (t < num_tiles) issue(t, s);
-    }
-  }
-
-  uint32_t phase = 0;
-  int stage = 0;
-  for (; tile < num_tiles; tile += warp_stride) {
-    const int ng = min(TG, B - tile * TG);
-    uint8_t* st = wbase + stage * ts.stage_bytes;
-    const T* Hs = reinterpret_cast<const T*>(st);
-    const T* As = reinterpret_cast<const T*>(st + ts.h_bytes);
-    uint32_t* Ms = reinterpret_cast<uint32_t*>(st + ts.h_bytes * (ADD ? 2 : 1));
-
-    if (((ng * N * 4) & 15) != 0) {    // ragged last tile: masks by plain loads
-      for (int i = lane; i < ng * N; i += 32) Ms[i] = mask[(size_t)tile * TG * N + i];
-      __syncwarp();
-    }
-    mbar_wait(&bars[warp][stage], (phase >> stage) & 1u);
-
-    uint32_t msk[MT];
-    float4 acc[MT];
-#pragma unroll
-    for (int j = 0; j < MT; ++j) {
-      const int m = j * MP + mp;
-      const bool ok = (m < N) && (gl < ng);
-      msk[j] = ok ? Ms[gl * N + m] : 0u;
-      if (ADD) {
-        acc[j] = ok ? ld_row4(As + ((size_t)(gl * N + m) * 16 + c * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      } else {
-        acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-    const T* hrow = Hs + (size_t)gl * N * 16 + c * 4;
-    if (gl < ng) {
-#pragma unroll 2
-      for (int n = 0; n < N; ++n) {
-        const float4 v = ld_row4(hrow + n * 16);
-        const uint32_t bit = 1u << n;
-#pragma unroll
-        for (int j = 0; j < MT; ++j) {
-          if (msk[j] & bit) add4(acc[j], v);
-        }
-      }
-    }
-    // previous tile's store must have finished reading out_s
-    if (lane == 0) bulk_wait_read<0>();
-    __syncwarp();
-    T* Os = reinterpret_cast<T*>(out_s);
-#pragma unroll
-    for (int j = 0; j < MT; ++j) {
-      const int m = j * MP + mp;
-      if (m < N) st_row4(Os + ((size_t)(gl * N + m) * 16 + c * 4), acc[j]);
-    }
-    fence_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      bulk_s2g(out + (size_t)tile * TG * graph_elems, out_s, (uint32_t)(ng * N * 16 * sizeof(T)));
-      bulk_commit();
-      const int nt = tile + kAggStages * warp_stride;   // refill the stage just consumed
-      if (nt < num_tiles) issue(nt, stage);
-    }
-    phase ^= (1u << stage);
-    stage = (stage + 1 == kAggStages) ? 0 : stage + 1;
-  }
-  if (lane == 0) bulk_wait<0>();
-}
 
 // ---------------------------------------------------------------------------
 // generic paths (any N <= 256, any F): one thread per output element
@@ -274,51 +109,30 @@ __global__ void adj_pack_kernel(const float* __restrict__ adj, int B, int N, int
 // ---------------------------------------------------------------------------
 // host dispatch
 // ---------------------------------------------------------------------------
+constexpr int kAggWarps = 8;        // warps per CTA (2 CTAs per SM when shared memory allows)
+
 template <typename T, int MT, int MP>
-static int launch_fast(const T* H, const uint32_t* mask, const T* addend, T* out, int B, int N,
+static int launch_fast(const T* H, const uint32_t* mask, const T* addend, T* out, int B, int N, bool independent,
                        cudaStream_t st) {
   constexpr int TG = 32 / (4 * MP);
-  const bool add = addend != nullptr;
-  AggTileSizes ts = agg_tile_sizes<T>(N, TG, add);
-  size_t smem = (size_t)ts.warp_bytes * kAggWarps;
-  int num_tiles = ceil_div(B, TG);
-  int grid = std::min(ceil_div(num_tiles, kAggWarps), sm_count());
-  if (add) {
-    auto k = agg_mask_f16_kernel<T, MT, MP, true>;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-      V2V_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set = smem;
-    }
-    k<<<grid, kAggWarps * 32, smem, st>>>(H, mask, addend, out, B, N);
-  } else {
-    auto k = agg_mask_f16_kernel<T, MT, MP, false>;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-      V2V_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set = smem;
-    }
-    k<<<grid, kAggWarps * 32, smem, st>>>(H, mask, addend, out, B, N);
-  }
-  return launch_status("agg_mask_f16_kernel");
-}
-
-template <typename T>
-static bool fast_fits(int N, int TG, bool add) {
-  AggTileSizes ts = agg_tile_sizes<T>(N, TG, add);
-  return (size_t)ts.warp_bytes * kAggWarps <= 226 * 1024;   // 227 KB minus the static mbarriers
+  AggLaunchCfg cfg;
+  cfg.dep_wait = !independent;
+  cfg.ctas_per_sm = agg_fast_fits<T>(N, TG, addend != nullptr, kAggWarps, 2) ? 2 : 1;
+  if (addend) return launch_agg_fast<T, MT, MP, true, kAggWarps>(H, mask, addend, out, B, N, cfg, st);
+  return launch_agg_fast<T, MT, MP, false, kAggWarps>(H, mask, addend, out, B, N, cfg, st);
 }
 
 template <typename T>
 static int agg_mask_dispatch(const T* H, const uint32_t* mask, const T* addend, T* out, int B, int N,
-                             int F, cudaStream_t st) {
+                             int F, bool independent, cudaStream_t st) {
   const bool aligned = ((((uintptr_t)H) | ((uintptr_t)out) | ((uintptr_t)mask) | ((uintptr_t)addend)) & 15u) == 0;
   const bool add = addend != nullptr;
   if (F == 16 && N <= 32 && aligned && B > 0) {
-    if (N <= 8 && fast_fits<T>(N, 8, add)) return launch_fast<T, 8, 1>(H, mask, addend, out, B, N, st);
-    if (N <= 20 && fast_fits<T>(N, 4, add)) return launch_fast<T, 10, 2>(H, mask, addend, out, B, N, st);
-    if (fast_fits<T>(N, 4, add)) return launch_fast<T, 16, 2>(H, mask, addend, out, B, N, st);
-    if (fast_fits<T>(N, 2, add)) return launch_fast<T, 8, 4>(H, mask, addend, out, B, N, st);
+    if (N <= 8 && agg_fast_fits<T>(N, 8, add, kAggWarps, 1)) return launch_fast<T, 8, 1>(H, mask, addend, out, B, N, independent, st);
+    // N <= 20: 2-graph tiles (16 lanes per graph, 5 targets per lane) pipeline best (profiles/agg_variants_r01.txt)
+    if (N <= 20 && agg_fast_fits<T>(N, 2, add, kAggWarps, 1)) return launch_fast<T, 5, 4>(H, mask, addend, out, B, N, independent, st);
+    if (agg_fast_fits<T>(N, 4, add, kAggWarps, 1)) return launch_fast<T, 16, 2>(H, mask, addend, out, B, N, independent, st);
+    if (agg_fast_fits<T>(N, 2, add, kAggWarps, 1)) return launch_fast<T, 8, 4>(H, mask, addend, out, B, N, independent, st);
   }
   const int W = ceil_div(N, 32);
   long total = (long)B * N * F;
@@ -333,20 +147,26 @@ static int agg_mask_dispatch(const T* H, const uint32_t* mask, const T* addend, 
 
 using namespace v2v;
 
-extern "C" int v2v_agg_mask(const void* H_dev, const uint32_t* mask_dev, const void* addend_dev,
-                            void* out_dev, int B, int N, int F, int dtype, void* stream) {
+extern "C" int v2v_agg_mask_ex(const void* H_dev, const uint32_t* mask_dev, const void* addend_dev,
+                               void* out_dev, int B, int N, int F, int dtype, unsigned flags, void* stream) {
   V2V_REQUIRE(B >= 0 && N > 0 && N <= 256 && F > 0, "v2v_agg_mask: bad shape B=%d N=%d F=%d", B, N, F);
+  const bool independent = (flags & V2V_AGG_INDEPENDENT) != 0;
   if (B == 0) return 0;
   V2V_REQUIRE(H_dev && mask_dev && out_dev, "v2v_agg_mask: null pointer");
   V2V_REQUIRE(H_dev != out_dev, "v2v_agg_mask: out must not alias H");
   V2V_REQUIRE(dtype == V2V_F32 || dtype == V2V_BF16, "v2v_agg_mask: unknown dtype %d", dtype);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == V2V_F32)
-    return agg_mask_dispatch<float>((const float*)H_dev, mask_dev, (const float*)addend_dev, (float*)out_dev, B, N, F, st);
+    return agg_mask_dispatch<float>((const float*)H_dev, mask_dev, (const float*)addend_dev, (float*)out_dev, B, N, F, independent, st);
   if (dtype == V2V_BF16)
     return agg_mask_dispatch<__nv_bfloat16>((const __nv_bfloat16*)H_dev, mask_dev, (const __nv_bfloat16*)addend_dev,
-                                            (__nv_bfloat16*)out_dev, B, N, F, st);
+                                            (__nv_bfloat16*)out_dev, B, N, F, independent, st);
   return fail("v2v_agg_mask: unknown dtype %d", dtype);
+}
+
+extern "C" int v2v_agg_mask(const void* H_dev, const uint32_t* mask_dev, const void* addend_dev,
+                            void* out_dev, int B, int N, int F, int dtype, void* stream) {
+  return v2v_agg_mask_ex(H_dev, mask_dev, addend_dev, out_dev, B, N, F, dtype, 0u, stream);
 }
 
 extern "C" int v2v_agg_dense(const float* H_dev, const float* adj_dev, const float* addend_dev,

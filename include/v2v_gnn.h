@@ -67,6 +67,14 @@ int v2v_adj_pack_masks(const float* adj_dev, int B, int N,
 int v2v_agg_mask(const void* H_dev, const uint32_t* mask_dev, const void* addend_dev,
                  void* out_dev, int B, int N, int F, int dtype, void* stream);
 
+/* Same operator with launch flags.  V2V_AGG_INDEPENDENT: the caller asserts that none of the
+ * operands is produced or still read by the kernel launched immediately before on `stream`
+ * (e.g. a stream of aggregations over distinct buffers); the kernel then skips the
+ * programmatic-dependent-launch wait and may overlap the tail of its predecessor. */
+#define V2V_AGG_INDEPENDENT 1u
+int v2v_agg_mask_ex(const void* H_dev, const uint32_t* mask_dev, const void* addend_dev,
+                    void* out_dev, int B, int N, int F, int dtype, unsigned flags, void* stream);
+
 /* Weighted (non 0/1) adjacency, fp32 only: adj_dev fp32 [B][N][N];
  * transpose = 0: out[b][m] = sum_n adj[b][n][m] H[b][n]   (forward)
  * transpose = 1: out[b][n] = sum_m adj[b][n][m] H[b][m]   (backward) */
