@@ -11,7 +11,9 @@
 #include <stdarg.h>
 #include <vector>
 
-#include "v2v_common.cuh"
+#include <map>
+
+#include "fused.cuh"
 
 namespace v2v {
 
@@ -78,7 +80,61 @@ struct v2v_brain {
   uint32_t* st_in_mask = nullptr; uint32_t* st_out_mask = nullptr;
   int* st_flag = nullptr;
   int* st_flag_host = nullptr;    // pinned
+  // fused whole-network path (shared weights, N <= 32, binary adjacency)
+  bool fused_capable = false;
+  bool fused_enabled = true;
+  std::vector<int> lK, lO;
+  std::vector<size_t> lw, lb;
+  struct FusedEntry { FusedProgram host; FusedProgram* dev = nullptr; };
+  std::map<long, FusedEntry*> fused_cache;      // key: (TG << 1) | train
+  std::map<long, int> tg_cache;                 // key: (B << 1) | train
+  float* partial = nullptr;                     // [sm_count][n_params] per-CTA gradient partials
+  int partial_ctas = 0;
+  int last_grid = 0;                            // grid of the last fused train launch (0: layered path ran)
+  bool defer_reduce = false;
 };
+
+static FusedShape fused_shape(const v2v_brain* b) {
+  FusedShape s;
+  s.N = b->N; s.Dn = b->Dn; s.De = b->De; s.F = b->F; s.CH = b->CH; s.S = b->S;
+  s.H1 = b->cfg.hidden[0]; s.H2 = b->cfg.hidden[1]; s.H3 = b->cfg.hidden[2];
+  s.layer_K = b->lK.data(); s.layer_O = b->lO.data(); s.w_off = b->lw.data(); s.b_off = b->lb.data();
+  s.n_layers = b->n_layers; s.n_params = b->n_params;
+  return s;
+}
+
+// program for (B, train), built and uploaded on first use (not during stream capture)
+static int fused_get(v2v_brain* b, int B, int train, v2v_brain::FusedEntry** out) {
+  const long bkey = ((long)B << 1) | train;
+  auto it = b->tg_cache.find(bkey);
+  int tg;
+  if (it == b->tg_cache.end()) {
+    tg = fused_pick_tg(fused_shape(b), B, train);
+    b->tg_cache[bkey] = tg;
+  } else {
+    tg = it->second;
+  }
+  V2V_REQUIRE(tg > 0, "fused path: no tile size fits shared memory");
+  const long key = ((long)tg << 1) | train;
+  auto ie = b->fused_cache.find(key);
+  if (ie == b->fused_cache.end()) {
+    auto* e = new v2v_brain::FusedEntry();
+    if (int rc = fused_build_program(fused_shape(b), tg, train, &e->host)) { delete e; return rc; }
+    if (cudaMalloc((void**)&e->dev, sizeof(FusedProgram)) != cudaSuccess) { delete e; return fail("fused path: cudaMalloc failed"); }
+    if (cudaMemcpy(e->dev, &e->host, sizeof(FusedProgram), cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaFree(e->dev); delete e; return fail("fused path: program upload failed");
+    }
+    b->fused_cache[key] = e;
+    *out = e;
+  } else {
+    *out = ie->second;
+  }
+  return 0;
+}
+
+static bool use_fused(const v2v_brain* b, const uint32_t* in_mask, const float* neigh) {
+  return b->fused_capable && b->fused_enabled && in_mask != nullptr && neigh == nullptr;
+}
 
 static int dmalloc(float** p, size_t n_floats) {
   V2V_CHECK_CUDA(cudaMalloc((void**)p, std::max<size_t>(n_floats, 1) * sizeof(float)));
@@ -101,6 +157,8 @@ extern "C" void v2v_brain_destroy(v2v_brain* b) {
   cudaFree(b->st_node); cudaFree(b->st_edge); cudaFree(b->st_neigh); cudaFree(b->st_adj); cudaFree(b->st_y); cudaFree(b->st_q);
   cudaFree(b->st_in_mask); cudaFree(b->st_out_mask); cudaFree(b->st_flag);
   if (b->st_flag_host) cudaFreeHost(b->st_flag_host);
+  cudaFree(b->partial);
+  for (auto& kv : b->fused_cache) { cudaFree(kv.second->dev); delete kv.second; }
   delete b;
 }
 
@@ -157,6 +215,19 @@ extern "C" int v2v_brain_create(const v2v_brain_config* cfg, v2v_brain** out) {
     return fail("v2v_brain_create: device allocation failed (%s)", e.c_str());
   }
   for (auto& p : b->params) cudaMemset(p, 0, b->n_params * sizeof(float));
+  for (auto& L : b->layers) { b->lK.push_back(L.K); b->lO.push_back(L.n_out); b->lw.push_back(L.w_off); b->lb.push_back(L.b_off); }
+  if (b->G == 1 && b->N <= 32) {
+    FusedProgram* probe = new FusedProgram();
+    if (fused_build_program(fused_shape(b), 1, 1, probe) == 0 && fused_smem_bytes(*probe) <= 226 * 1024) {
+      b->partial_ctas = sm_count();
+      if (cudaMalloc((void**)&b->partial, (size_t)b->partial_ctas * b->n_params * sizeof(float)) == cudaSuccess) {
+        cudaMemset(b->partial, 0, (size_t)b->partial_ctas * b->n_params * sizeof(float));
+        b->fused_capable = true;
+      }
+    }
+    delete probe;
+    last_error().clear();
+  }
   *out = b;
   return 0;
 }
@@ -186,6 +257,57 @@ extern "C" int v2v_brain_set_params(v2v_brain* b, int which, const float* host_i
   V2V_CHECK_CUDA(cudaMemcpyAsync(b->params[which], host_in, b->n_params * sizeof(float), cudaMemcpyHostToDevice, st));
   V2V_CHECK_CUDA(cudaStreamSynchronize(st));
   return 0;
+}
+
+extern "C" int v2v_brain_set_fused(v2v_brain* b, int enable) {
+  V2V_REQUIRE(b, "v2v_brain_set_fused: null brain");
+  b->fused_enabled = enable != 0;
+  return 0;
+}
+
+extern "C" int v2v_brain_fused_info(v2v_brain* b, int B, int train, int* info8) {
+  V2V_REQUIRE(b && info8 && B > 0, "v2v_brain_fused_info: bad argument");
+  for (int i = 0; i < 8; ++i) info8[i] = 0;
+  if (!b->fused_capable) return 0;
+  FusedProgram* p = new FusedProgram();
+  const int tg = fused_pick_tg(fused_shape(b), B, train);
+  int rc = tg > 0 ? fused_build_program(fused_shape(b), tg, train, p) : 1;
+  if (rc == 0) {
+    info8[0] = 1; info8[1] = tg; info8[2] = p->n_rows; info8[3] = (int)fused_smem_bytes(*p); info8[4] = p->n_ops;
+    info8[5] = p->n_blocks; info8[6] = p->n_bias; info8[7] = p->n_tab;
+  }
+  delete p;
+  return rc;
+}
+
+// Host-only planning query (no device needed): the fused program a brain of this configuration would
+// run for a batch of B graphs.  info8 as in v2v_brain_fused_info.
+extern "C" int v2v_fused_plan(const v2v_brain_config* cfg, int B, int train, int* info8) {
+  V2V_REQUIRE(cfg && info8 && B > 0, "v2v_fused_plan: bad argument");
+  for (int i = 0; i < 8; ++i) info8[i] = 0;
+  if (cfg->per_slot || cfg->num_d2d > 32) return 0;
+  std::vector<int> lK, lO;
+  std::vector<size_t> lw, lb;
+  size_t off = 0;
+  auto add_layer = [&](int K, int O) { lK.push_back(K); lO.push_back(O); lw.push_back(off); off += (size_t)K * O; lb.push_back(off); off += O; };
+  for (int s = 0; s < cfg->stages; ++s) add_layer((s == 0 ? cfg->node_dim : cfg->feedback + cfg->node_dim) + cfg->edge_dim + cfg->feedback, cfg->feedback);
+  int k = cfg->node_dim + 2 * cfg->feedback;
+  for (int i = 0; i < 3; ++i) { add_layer(k, cfg->hidden[i]); k = cfg->hidden[i]; }
+  add_layer(k, cfg->num_ch);
+  FusedShape s;
+  s.N = cfg->num_d2d; s.Dn = cfg->node_dim; s.De = cfg->edge_dim; s.F = cfg->feedback; s.CH = cfg->num_ch; s.S = cfg->stages;
+  s.H1 = cfg->hidden[0]; s.H2 = cfg->hidden[1]; s.H3 = cfg->hidden[2];
+  s.layer_K = lK.data(); s.layer_O = lO.data(); s.w_off = lw.data(); s.b_off = lb.data();
+  s.n_layers = (int)lK.size(); s.n_params = off;
+  FusedProgram* p = new FusedProgram();
+  const int tg = fused_pick_tg(s, B, train);
+  int rc = tg > 0 ? fused_build_program(s, tg, train, p) : 0;
+  if (rc == 0 && tg > 0) {
+    info8[0] = 1; info8[1] = tg; info8[2] = p->n_rows; info8[3] = (int)fused_smem_bytes(*p); info8[4] = p->n_ops;
+    info8[5] = p->n_blocks; info8[6] = p->n_bias; info8[7] = p->n_tab;
+  }
+  delete p;
+  return rc;
 }
 
 extern "C" int v2v_brain_update_target(v2v_brain* b, void* stream) {
@@ -250,6 +372,12 @@ extern "C" int v2v_brain_forward(v2v_brain* b, const float* node_dev, const floa
   if (B == 0) return 0;
   V2V_REQUIRE(node_dev && edge_dev && q_dev, "v2v_brain_forward: null pointer");
   V2V_REQUIRE(in_mask_dev || adj_dev, "v2v_brain_forward: need in_mask or adj");
+  if (use_fused(b, in_mask_dev, neighbor_dev)) {
+    v2v_brain::FusedEntry* e = nullptr;
+    if (int rc = fused_get(b, B, 0, &e)) return rc;
+    return fused_launch(e->host, e->dev, b->params[target ? 1 : 0], node_dev, edge_dev, in_mask_dev, nullptr, q_dev, nullptr,
+                        nullptr, B, fused_grid(e->host, B), (cudaStream_t)stream);
+  }
   return forward_impl(b, b->params[target ? 1 : 0], node_dev, edge_dev, neighbor_dev, in_mask_dev, adj_dev, B, q_dev, stream);
 }
 
@@ -270,6 +398,17 @@ extern "C" int v2v_brain_forward_backward(v2v_brain* b, const float* node, const
   float* Gd = b->params[2];
   float* hl = head_loss_dev ? head_loss_dev : b->head_loss;
 
+  if (use_fused(b, im, neigh)) {
+    v2v_brain::FusedEntry* e = nullptr;
+    if (int rc = fused_get(b, B, 1, &e)) return rc;
+    V2V_CHECK_CUDA(cudaMemsetAsync(hl, 0, N * sizeof(float), st));
+    const int grid = fused_grid(e->host, B);
+    b->last_grid = grid;
+    if (int rc = fused_launch(e->host, e->dev, P, node, edge, im, y, nullptr, b->partial, hl, B, grid, st)) return rc;
+    if (b->defer_reduce) return 0;      // train_step fuses the reduction with Adam
+    return fused_reduce_adam(b->partial, grid, Gd, nullptr, nullptr, nullptr, (long)b->n_params, 0, 0.f, 0.f, 0.f, 0.f, 1.f, st);
+  }
+  b->last_grid = 0;
   if (int rc = forward_impl(b, P, node, edge, neigh, im, adj, B, nullptr, stream)) return rc;
   V2V_CHECK_CUDA(cudaMemsetAsync(Gd, 0, b->n_params * sizeof(float), st));
   V2V_CHECK_CUDA(cudaMemsetAsync(hl, 0, N * sizeof(float), st));
@@ -328,7 +467,16 @@ extern "C" int v2v_brain_apply_adam(v2v_brain* b, float grad_scale, void* stream
 extern "C" int v2v_brain_train_step(v2v_brain* b, const float* node, const float* edge,
                                     const float* neigh, const uint32_t* in_mask, const uint32_t* out_mask, const float* adj,
                                     const float* y, int B, float* head_loss_dev, void* stream) {
-  if (int rc = v2v_brain_forward_backward(b, node, edge, neigh, in_mask, out_mask, adj, y, B, head_loss_dev, stream)) return rc;
+  b->defer_reduce = true;
+  int rc = v2v_brain_forward_backward(b, node, edge, neigh, in_mask, out_mask, adj, y, B, head_loss_dev, stream);
+  b->defer_reduce = false;
+  if (rc) return rc;
+  if (b->last_grid > 0) {             // fused path: partial reduction + Keras-Adam in one kernel
+    b->iterations += 1;
+    return fused_reduce_adam(b->partial, b->last_grid, b->params[2], b->params[0], b->params[3], b->params[4],
+                             (long)b->n_params, b->iterations, b->cfg.lr, b->cfg.beta1, b->cfg.beta2, b->cfg.eps, 1.f,
+                             (cudaStream_t)stream);
+  }
   return v2v_brain_apply_adam(b, 1.f, stream);
 }
 
@@ -360,9 +508,8 @@ extern "C" int v2v_brain_predict_host(v2v_brain* b, const float* node_host, cons
   cudaStream_t st = (cudaStream_t)stream;
   bool weighted = false;
   if (int rc = stage_inputs(b, node_host, edge_host, neigh_host, adj_host, B, false, &weighted, st)) return rc;
-  if (int rc = forward_impl(b, b->params[target ? 1 : 0], b->st_node, b->st_edge, neigh_host ? b->st_neigh : nullptr,
-                            weighted ? nullptr : b->st_in_mask,
-                            b->st_adj, B, b->st_q, stream)) return rc;
+  if (int rc = v2v_brain_forward(b, b->st_node, b->st_edge, neigh_host ? b->st_neigh : nullptr,
+                                 weighted ? nullptr : b->st_in_mask, b->st_adj, B, target, b->st_q, stream)) return rc;
   V2V_CHECK_CUDA(cudaMemcpyAsync(q_host, b->st_q, (size_t)B * b->N * b->CH * sizeof(float), cudaMemcpyDeviceToHost, st));
   V2V_CHECK_CUDA(cudaStreamSynchronize(st));
   return 0;

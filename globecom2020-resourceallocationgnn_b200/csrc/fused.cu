@@ -1,0 +1,652 @@
+// Whole-network fused kernel for the shared-weight brain (G == 1, N <= 32):
+//   forward (BS_brain.py:147-200) + Huber head (:86-87) + full backward in ONE launch.
+//
+// A CTA owns tiles of TG whole graphs (R = TG*N node rows).  Every activation of the tile lives in a
+// feature-major shared-memory arena  arena[feature_row][RP]  (row index fastest), so
+//   * a layer is out[o][r] = sum_k W[k][o] * in[k][r]: the thread tile (4 rows x 4..8 columns) reads ONE
+//     128-bit shared-memory vector of activations and one/two broadcast vectors of weights per k and
+//     issues 16..32 FFMA -- true fp32 (the 1e-4 parity bar rules out single-pass TF32);
+//   * the concatenations of the reference ([h|node|edge|agg], [node|h|agg]) are just row lists;
+//   * the neighbour aggregation is a register gather-reduce over the 20 rows of a graph inside the
+//     arena: no HBM traffic at all (the standalone kernel in agg.cu serves the AggLayer surface);
+//   * backward re-uses dead forward rows for the data gradients; the weight-gradient 4x4 blocks of
+//     all layers are spread over the threads, accumulated in registers across the CTA's tiles and
+//     written once as a per-CTA partial (deterministic; reduced by fused_reduce_adam).
+// HBM traffic per graph (N=20): 1,040 B features + 80 B mask + 320 B targets in; nothing out but the
+// 35 KB gradient partial per CTA.
+#include <algorithm>
+#include <vector>
+
+#include "fused.cuh"
+
+namespace v2v {
+
+// ---------------------------------------------------------------------------
+// device side
+// ---------------------------------------------------------------------------
+template <int TR>
+struct RowVec;
+template <>
+struct RowVec<4> {
+  float v[4];
+  __device__ __forceinline__ void load(const float* p) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <>
+struct RowVec<2> {
+  float v[2];
+  __device__ __forceinline__ void load(const float* p) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    v[0] = t.x; v[1] = t.y;
+  }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+};
+
+template <int TR, int TC>
+__device__ __forceinline__ void gemm_phase(const FusedOp& op, float* arena, const float* Ws, const int* tab, int RP,
+                                           int tid) {
+  const int row_groups = RP / TR;
+  const int items = row_groups * (op.O / TC);
+  const int* in_rows = tab + op.in_tab;
+  const int* out_rows = tab + op.out_tab;
+  for (int item = tid; item < items; item += kFusedThreads) {
+    const int cg = item / row_groups, rg = item - cg * row_groups;
+    const int r0 = rg * TR, o0 = cg * TC;
+    float acc[TC][TR];
+#pragma unroll
+    for (int j = 0; j < TC; ++j) {
+      const float b = Ws[op.b_off + o0 + j];
+#pragma unroll
+      for (int i = 0; i < TR; ++i) acc[j][i] = b;
+    }
+    const float* wp = Ws + op.w_off + o0;
+#pragma unroll 2
+    for (int k = 0; k < op.K; ++k) {
+      RowVec<TR> x;
+      x.load(arena + in_rows[k] * RP + r0);
+      float w[TC];
+#pragma unroll
+      for (int j4 = 0; j4 < TC; j4 += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(wp + k * op.O + j4);
+        w[j4] = t.x; w[j4 + 1] = t.y; w[j4 + 2] = t.z; w[j4 + 3] = t.w;
+      }
+#pragma unroll
+      for (int j = 0; j < TC; ++j)
+#pragma unroll
+        for (int i = 0; i < TR; ++i) acc[j][i] = fmaf(x.v[i], w[j], acc[j][i]);
+    }
+#pragma unroll
+    for (int j = 0; j < TC; ++j) {
+      RowVec<TR> o;
+#pragma unroll
+      for (int i = 0; i < TR; ++i) o.v[i] = op.relu ? fmaxf(acc[j][i], 0.f) : acc[j][i];
+      o.store(arena + out_rows[o0 + j] * RP + r0);
+    }
+  }
+}
+
+// Neighbour aggregation inside the arena.  item = (feature f, graph g, target split ms).
+template <int NMAX>
+__device__ __forceinline__ void agg_phase(const FusedOp& op, float* arena, const int* tab, const uint32_t* mask_s, int RP,
+                                          int N, int TG, int tid) {
+  constexpr int MS = 3;
+  constexpr int MT = (NMAX + MS - 1) / MS;
+  const int F = op.K;
+  const int items = F * TG * MS;
+  for (int item = tid; item < items; item += kFusedThreads) {
+    const int f = item % F;
+    const int rest = item / F;
+    const int g = rest % TG, ms = rest / TG;
+    const float* src = arena + tab[op.in_tab + f] * RP + g * N;
+    float v[NMAX];
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) v[n] = (n < N) ? src[n] : 0.f;
+    float acc[MT];
+#pragma unroll
+    for (int j = 0; j < MT; ++j) acc[j] = 0.f;
+    if (!op.transposed) {
+#pragma unroll
+      for (int j = 0; j < MT; ++j) {
+        const int m = ms + j * MS;
+        const uint32_t msk = (m < N) ? mask_s[g * N + m] : 0u;
+#pragma unroll
+        for (int n = 0; n < NMAX; ++n)
+          if (msk & (1u << n)) acc[j] += v[n];
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < NMAX; ++m) {
+        const uint32_t msk = (m < N) ? mask_s[g * N + m] : 0u;
+#pragma unroll
+        for (int j = 0; j < MT; ++j)
+          if (msk & (1u << ((ms + j * MS) & 31))) acc[j] += v[m];
+      }
+    }
+    float* dst = arena + tab[op.out_tab + f] * RP + g * N;
+    const float* add = op.add_tab >= 0 ? arena + tab[op.add_tab + f] * RP + g * N : nullptr;
+    const float* gate = op.gate_tab >= 0 ? arena + tab[op.gate_tab + f] * RP + g * N : nullptr;
+#pragma unroll
+    for (int j = 0; j < MT; ++j) {
+      const int m = ms + j * MS;
+      if (m < N) {
+        float r = acc[j];
+        if (add) r += add[m];
+        if (gate) r = gate[m] > 0.f ? r : 0.f;
+        dst[m] = r;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void loss_phase(const FusedProgram* P, float* arena, const int* tab, float* hl_s, int RP,
+                                           int valid_rows, float inv_cnt, int tid) {
+  const int items = P->CH * RP;
+  for (int item = tid; item < items; item += kFusedThreads) {
+    const int c = item / RP, r = item - c * RP;
+    float* q = arena + tab[P->q_tab + c] * RP + r;
+    const float yv = arena[tab[P->y_tab + c] * RP + r];
+    float dq = 0.f;
+    if (r < valid_rows) {
+      const float e = *q - yv;
+      const float ae = fabsf(e);
+      const float quad = fminf(ae, 1.f);
+      atomicAdd(&hl_s[r % P->N], 0.5f * quad * quad + (ae - quad));
+      dq = fminf(fmaxf(e, -1.f), 1.f) * inv_cnt;
+    }
+    *q = dq;
+  }
+}
+
+__device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* arena, const float* Ws, const int* tab, int RP,
+                                          int zero_row, int tid, const int (&my_blk)[kFusedBlkPerThread],
+                                          float (&wacc)[kFusedBlkPerThread][16], int my_bias, float& bacc) {
+  // ---- weight-gradient blocks owned by this thread that belong to this layer
+#pragma unroll
+  for (int s = 0; s < kFusedBlkPerThread; ++s) {
+    const int b = tid + s * kFusedThreads;
+    if (b >= op.blk0 && b < op.blk0 + op.nblk) {
+      const int kb = (my_blk[s] >> 8) & 0xff, ob = my_blk[s] & 0xff;
+      const float* xr[4];
+      const float* dr[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = kb * 4 + i;
+        xr[i] = arena + (k < op.K ? tab[op.in_tab + k] : zero_row) * RP;
+        dr[i] = arena + tab[op.dz_tab + ob * 4 + i] * RP;
+      }
+      float a[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] = 0.f;
+      for (int r = 0; r < RP; r += 4) {
+        float4 xv[4], dv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          xv[i] = *reinterpret_cast<const float4*>(xr[i] + r);
+          dv[i] = *reinterpret_cast<const float4*>(dr[i] + r);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float t = a[i * 4 + j];
+            t = fmaf(xv[i].x, dv[j].x, t); t = fmaf(xv[i].y, dv[j].y, t);
+            t = fmaf(xv[i].z, dv[j].z, t); t = fmaf(xv[i].w, dv[j].w, t);
+            a[i * 4 + j] = t;
+          }
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) wacc[s][i] += a[i];
+    }
+  }
+  // ---- bias gradient slot
+  if (my_bias >= 0 && (my_bias >> 16) == op_idx) {
+    const float* dz = arena + tab[op.dz_tab + (my_bias & 0xffff)] * RP;
+    float s = 0.f;
+    for (int r = 0; r < RP; r += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(dz + r);
+      s += (t.x + t.y) + (t.z + t.w);
+    }
+    bacc += s;
+  }
+  // ---- data gradient of the requested input columns (4 rows x 4 columns per item)
+  if (op.n_dx > 0) {
+    const int row_groups = RP / 4;
+    const int items = row_groups * (op.n_dx / 4);
+    for (int item = kFusedThreads - 1 - tid; item < items; item += kFusedThreads) {
+      const int kg = item / row_groups, rg = item - kg * row_groups;
+      const int r0 = rg * 4;
+      const float* wr[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) wr[i] = Ws + op.w_off + tab[op.dxk_tab + kg * 4 + i] * op.O;
+      float4 acc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int o = 0; o < op.O; o += 4) {
+        float4 dz[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dz[j] = *reinterpret_cast<const float4*>(arena + tab[op.dz_tab + o + j] * RP + r0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 w = *reinterpret_cast<const float4*>(wr[i] + o);
+          acc[i].x = fmaf(dz[0].x, w.x, acc[i].x); acc[i].y = fmaf(dz[0].y, w.x, acc[i].y);
+          acc[i].z = fmaf(dz[0].z, w.x, acc[i].z); acc[i].w = fmaf(dz[0].w, w.x, acc[i].w);
+          acc[i].x = fmaf(dz[1].x, w.y, acc[i].x); acc[i].y = fmaf(dz[1].y, w.y, acc[i].y);
+          acc[i].z = fmaf(dz[1].z, w.y, acc[i].z); acc[i].w = fmaf(dz[1].w, w.y, acc[i].w);
+          acc[i].x = fmaf(dz[2].x, w.z, acc[i].x); acc[i].y = fmaf(dz[2].y, w.z, acc[i].y);
+          acc[i].z = fmaf(dz[2].z, w.z, acc[i].z); acc[i].w = fmaf(dz[2].w, w.z, acc[i].w);
+          acc[i].x = fmaf(dz[3].x, w.w, acc[i].x); acc[i].y = fmaf(dz[3].y, w.w, acc[i].y);
+          acc[i].z = fmaf(dz[3].z, w.w, acc[i].z); acc[i].w = fmaf(dz[3].w, w.w, acc[i].w);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 v = acc[i];
+        if (op.gate_tab >= 0) {
+          const float4 g = *reinterpret_cast<const float4*>(arena + tab[op.gate_tab + kg * 4 + i] * RP + r0);
+          v.x = g.x > 0.f ? v.x : 0.f; v.y = g.y > 0.f ? v.y : 0.f;
+          v.z = g.z > 0.f ? v.z : 0.f; v.w = g.w > 0.f ? v.w : 0.f;
+        }
+        *reinterpret_cast<float4*>(arena + tab[op.dx_tab + kg * 4 + i] * RP + r0) = v;
+      }
+    }
+  }
+}
+
+template <int NMAX>
+__global__ void __launch_bounds__(kFusedThreads, 1)
+fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__ params, const float* __restrict__ node,
+                   const float* __restrict__ edge, const uint32_t* __restrict__ in_mask, const float* __restrict__ y,
+                   float* __restrict__ q_out, float* __restrict__ partial, float* __restrict__ head_loss, int B,
+                   float inv_cnt) {
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x;
+  const int N = P->N, TG = P->TG, RP = P->RP, CH = P->CH, Dn = P->Dn, De = P->De;
+  const int n_params = P->n_params, n_ops = P->n_ops, n_tab = P->n_tab, train = P->train;
+  const int np_pad = (n_params + 3) & ~3;
+  float* Ws = smem;
+  int* tab = reinterpret_cast<int*>(Ws + np_pad);
+  FusedOp* ops = reinterpret_cast<FusedOp*>(tab + ((n_tab + 3) & ~3));
+  uint32_t* mask_s = reinterpret_cast<uint32_t*>(ops + n_ops);
+  float* hl_s = reinterpret_cast<float*>(mask_s + ((TG * N + 3) & ~3));
+  float* arena = hl_s + 32;
+
+  for (int i = tid; i < n_params / 4; i += kFusedThreads)
+    reinterpret_cast<float4*>(Ws)[i] = reinterpret_cast<const float4*>(params)[i];
+  for (int i = (n_params & ~3) + tid; i < n_params; i += kFusedThreads) Ws[i] = params[i];
+  for (int i = tid; i < n_tab; i += kFusedThreads) tab[i] = P->tab[i];
+  {
+    const int words = n_ops * (int)(sizeof(FusedOp) / 4);
+    const int* src = reinterpret_cast<const int*>(P->ops);
+    int* dst = reinterpret_cast<int*>(ops);
+    for (int i = tid; i < words; i += kFusedThreads) dst[i] = src[i];
+  }
+  if (tid < 32) hl_s[tid] = 0.f;
+  for (int i = tid; i < RP; i += kFusedThreads) arena[P->zero_row * RP + i] = 0.f;
+
+  int my_blk[kFusedBlkPerThread];
+  float wacc[kFusedBlkPerThread][16];
+#pragma unroll
+  for (int s = 0; s < kFusedBlkPerThread; ++s) {
+    const int b = tid + s * kFusedThreads;
+    my_blk[s] = (train && b < P->n_blocks) ? P->blk_info[b] : 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) wacc[s][i] = 0.f;
+  }
+  const int bias_slot = kFusedThreads - 1 - tid;
+  const int my_bias = (train && bias_slot < P->n_bias) ? P->bias_info[bias_slot] : -1;
+  float bacc = 0.f;
+
+  const int n_tiles = (B + TG - 1) / TG;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int g0 = tile * TG;
+    const int ng = min(TG, B - g0);
+    const int valid_rows = ng * N;
+    __syncthreads();                         // previous tile fully consumed (and the prologue stores)
+    {
+      const float* nsrc = node + (size_t)g0 * N * Dn;
+      for (int idx = tid; idx < RP * Dn; idx += kFusedThreads) {
+        const int r = idx / Dn, f = idx - r * Dn;
+        arena[(P->x0_row0 + f) * RP + r] = (r < valid_rows) ? nsrc[idx] : 0.f;
+      }
+      const float* esrc = edge + (size_t)g0 * N * De;
+      for (int idx = tid; idx < RP * De; idx += kFusedThreads) {
+        const int r = idx / De, f = idx - r * De;
+        arena[(P->x0_row0 + Dn + f) * RP + r] = (r < valid_rows) ? esrc[idx] : 0.f;
+      }
+      for (int idx = tid; idx < TG * N; idx += kFusedThreads)
+        mask_s[idx] = (idx < valid_rows) ? in_mask[(size_t)g0 * N + idx] : 0u;
+      if (train) {
+        const float* ysrc = y + (size_t)g0 * N * CH;
+        for (int idx = tid; idx < RP * CH; idx += kFusedThreads) {
+          const int r = idx / CH, c = idx - r * CH;
+          arena[tab[P->y_tab + c] * RP + r] = (r < valid_rows) ? ysrc[idx] : 0.f;
+        }
+      }
+    }
+    __syncthreads();
+    for (int oi = 0; oi < n_ops; ++oi) {
+      const FusedOp& op = ops[oi];
+      switch (op.type) {
+        case FOP_GEMM: {
+          const int rg4 = RP / 4;
+          if (op.O % 8 == 0 && rg4 * (op.O / 8) >= (kFusedThreads * 3) / 4) gemm_phase<4, 8>(op, arena, Ws, tab, RP, tid);
+          else if (rg4 * (op.O / 4) >= kFusedThreads / 2) gemm_phase<4, 4>(op, arena, Ws, tab, RP, tid);
+          else gemm_phase<2, 4>(op, arena, Ws, tab, RP, tid);
+          break;
+        }
+        case FOP_AGG: agg_phase<NMAX>(op, arena, tab, mask_s, RP, N, TG, tid); break;
+        case FOP_LOSS: loss_phase(P, arena, tab, hl_s, RP, valid_rows, inv_cnt, tid); break;
+        case FOP_BWD: bwd_phase(op, oi, arena, Ws, tab, RP, P->zero_row, tid, my_blk, wacc, my_bias, bacc); break;
+        default: break;
+      }
+      __syncthreads();
+    }
+    if (!train) {
+      float* qdst = q_out + (size_t)g0 * N * CH;
+      for (int idx = tid; idx < valid_rows * CH; idx += kFusedThreads) {
+        const int r = idx / CH, c = idx - r * CH;
+        qdst[idx] = arena[tab[P->q_tab + c] * RP + r];
+      }
+    }
+  }
+
+  if (train) {
+    float* dst = partial + (size_t)blockIdx.x * n_params;
+#pragma unroll
+    for (int s = 0; s < kFusedBlkPerThread; ++s) {
+      const int b = tid + s * kFusedThreads;
+      if (b < P->n_blocks) {
+        const FusedOp& op = ops[my_blk[s] >> 16];
+        const int kb = (my_blk[s] >> 8) & 0xff, ob = my_blk[s] & 0xff;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int k = kb * 4 + i;
+          if (k < op.K)
+            *reinterpret_cast<float4*>(dst + op.w_off + k * op.O + ob * 4) =
+                make_float4(wacc[s][i * 4], wacc[s][i * 4 + 1], wacc[s][i * 4 + 2], wacc[s][i * 4 + 3]);
+        }
+      }
+    }
+    if (my_bias >= 0) dst[ops[my_bias >> 16].b_off + (my_bias & 0xffff)] = bacc;
+    __syncthreads();
+    if (tid < N && hl_s[tid] != 0.f) atomicAdd(&head_loss[tid], hl_s[tid] * inv_cnt);
+  }
+}
+
+__global__ void reduce_adam_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ grad,
+                                   float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, long n, int do_adam,
+                                   float lr_t, float b1, float b2, float eps, float gscale) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+  int c = 0;
+  for (; c + 4 <= n_cta; c += 4) {
+    g0 += partial[(long)c * n + i];
+    g1 += partial[(long)(c + 1) * n + i];
+    g2 += partial[(long)(c + 2) * n + i];
+    g3 += partial[(long)(c + 3) * n + i];
+  }
+  for (; c < n_cta; ++c) g0 += partial[(long)c * n + i];
+  const float g = (g0 + g1) + (g2 + g3);
+  grad[i] = g;
+  if (do_adam) {
+    const float gi = g * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side: program builder
+// ---------------------------------------------------------------------------
+namespace {
+
+struct Builder {
+  FusedProgram* P;
+  std::vector<int> free_rows;
+  int next_row = 0;
+  bool overflow = false;
+
+  int tab_put(const std::vector<int>& rows) {
+    const int off = P->n_tab;
+    if (off + (int)rows.size() > kFusedMaxTab) { overflow = true; return 0; }
+    for (int r : rows) P->tab[P->n_tab++] = r;
+    return off;
+  }
+  std::vector<int> fresh(int n) {
+    std::vector<int> v(n);
+    for (int i = 0; i < n; ++i) v[i] = next_row++;
+    return v;
+  }
+  std::vector<int> take(int n) {                 // re-use dead rows first
+    std::vector<int> v;
+    while ((int)v.size() < n && !free_rows.empty()) { v.push_back(free_rows.back()); free_rows.pop_back(); }
+    while ((int)v.size() < n) v.push_back(next_row++);
+    return v;
+  }
+  void release(const std::vector<int>& rows) { free_rows.insert(free_rows.end(), rows.begin(), rows.end()); }
+  FusedOp* add_op() {
+    if (P->n_ops >= kFusedMaxOps) { overflow = true; return &P->ops[0]; }
+    FusedOp* op = &P->ops[P->n_ops++];
+    *op = FusedOp{};
+    op->add_tab = op->gate_tab = -1;
+    return op;
+  }
+};
+
+std::vector<int> cat(std::initializer_list<std::vector<int>> parts) {
+  std::vector<int> v;
+  for (auto& p : parts) v.insert(v.end(), p.begin(), p.end());
+  return v;
+}
+std::vector<int> iota(int first, int n) {
+  std::vector<int> v(n);
+  for (int i = 0; i < n; ++i) v[i] = first + i;
+  return v;
+}
+
+}  // namespace
+
+int fused_build_program(const FusedShape& s, int TG, int train, FusedProgram* out) {
+  V2V_REQUIRE(s.N <= 32 && s.F % 4 == 0 && s.CH % 4 == 0 && s.H1 % 4 == 0 && s.H2 % 4 == 0 && s.H3 % 4 == 0,
+              "fused path: unsupported dimensions");
+  V2V_REQUIRE(s.n_layers == s.S + 4 && s.S >= 1, "fused path: unexpected layer count");
+  for (int l = 0; l < s.n_layers; ++l)
+    V2V_REQUIRE(s.w_off[l] % 4 == 0 && s.b_off[l] % 4 == 0 && s.layer_K[l] <= 255 && s.layer_O[l] <= 1020,
+                "fused path: unaligned parameter layout");
+  FusedProgram* P = out;
+  *P = FusedProgram{};
+  P->N = s.N; P->TG = TG; P->R = TG * s.N; P->RP = (P->R + 3) & ~3; P->CH = s.CH; P->F = s.F;
+  P->Dn = s.Dn; P->De = s.De; P->n_params = (int)s.n_params; P->train = train;
+  Builder b; b.P = P;
+  const int F = s.F, Dn = s.Dn, De = s.De, S = s.S;
+
+  P->zero_row = b.fresh(1)[0];
+  std::vector<int> x0 = b.fresh(Dn + De);
+  P->x0_row0 = x0[0];
+  std::vector<int> nodeR(x0.begin(), x0.begin() + Dn), edgeR(x0.begin() + Dn, x0.end());
+  std::vector<std::vector<int>> h(S), a(S);
+  std::vector<std::vector<int>> gemm_in(s.n_layers);
+  // ---- forward
+  for (int st = 0; st < S; ++st) {
+    h[st] = b.fresh(F);
+    a[st] = b.fresh(F);
+    gemm_in[st] = (st == 0) ? x0 : cat({h[st - 1], nodeR, edgeR, a[st - 1]});
+    FusedOp* g = b.add_op();
+    g->type = FOP_GEMM; g->in_tab = b.tab_put(gemm_in[st]); g->K = (int)gemm_in[st].size();
+    g->out_tab = b.tab_put(h[st]); g->O = F; g->w_off = (int)s.w_off[st]; g->b_off = (int)s.b_off[st];
+    g->relu = st < S - 1;
+    FusedOp* ag = b.add_op();
+    ag->type = FOP_AGG; ag->in_tab = b.tab_put(h[st]); ag->K = F; ag->out_tab = b.tab_put(a[st]); ag->O = F;
+  }
+  const int widths[4] = {s.H1, s.H2, s.H3, s.CH};
+  std::vector<std::vector<int>> mrows(4);
+  for (int j = 0; j < 4; ++j) {
+    const int l = S + j;
+    mrows[j] = b.fresh(widths[j]);
+    gemm_in[l] = (j == 0) ? cat({nodeR, h[S - 1], a[S - 1]}) : mrows[j - 1];
+    V2V_REQUIRE((int)gemm_in[l].size() == s.layer_K[l], "fused path: layer %d input width mismatch", l);
+    FusedOp* g = b.add_op();
+    g->type = FOP_GEMM; g->in_tab = b.tab_put(gemm_in[l]); g->K = (int)gemm_in[l].size();
+    g->out_tab = b.tab_put(mrows[j]); g->O = widths[j]; g->w_off = (int)s.w_off[l]; g->b_off = (int)s.b_off[l];
+    g->relu = j < 3;
+  }
+  P->q_tab = b.tab_put(mrows[3]);
+  if (train) {
+    std::vector<int> yR = b.fresh(s.CH);
+    P->y_tab = b.tab_put(yR);
+    FusedOp* lo = b.add_op();
+    lo->type = FOP_LOSS;
+    b.release(yR);   // dead after the loss phase
+    int blk = 0, bias = 0;
+    auto add_bwd = [&](int l, const std::vector<int>& dz, const std::vector<int>& dxk, const std::vector<int>& dx,
+                       const std::vector<int>& gate) -> int {
+      FusedOp* o = b.add_op();
+      const int op_idx = P->n_ops - 1;
+      o->type = FOP_BWD;
+      o->in_tab = b.tab_put(gemm_in[l]); o->K = (int)gemm_in[l].size();
+      o->O = s.layer_O[l]; o->w_off = (int)s.w_off[l]; o->b_off = (int)s.b_off[l];
+      o->dz_tab = b.tab_put(dz);
+      o->n_dx = (int)dxk.size();
+      if (o->n_dx) { o->dxk_tab = b.tab_put(dxk); o->dx_tab = b.tab_put(dx); }
+      o->gate_tab = gate.empty() ? -1 : b.tab_put(gate);
+      o->blk0 = blk;
+      const int kb_n = (o->K + 3) / 4, ob_n = o->O / 4;
+      o->nblk = kb_n * ob_n;
+      for (int kb = 0; kb < kb_n; ++kb)
+        for (int ob = 0; ob < ob_n; ++ob) {
+          if (blk >= kFusedThreads * kFusedBlkPerThread) { b.overflow = true; break; }
+          P->blk_info[blk++] = (op_idx << 16) | (kb << 8) | ob;
+        }
+      o->bias0 = bias;
+      for (int oo = 0; oo < o->O; ++oo) {
+        if (bias >= kFusedThreads) { b.overflow = true; break; }
+        P->bias_info[bias++] = (op_idx << 16) | oo;
+      }
+      return op_idx;
+    };
+    // decision MLP, last layer first; dz of layer j lives in `dz`
+    std::vector<int> dz = mrows[3];                               // dq in place over q
+    for (int j = 3; j >= 1; --j) {
+      std::vector<int> dx = b.take(widths[j - 1]);
+      add_bwd(S + j, dz, iota(0, widths[j - 1]), dx, mrows[j - 1]);
+      b.release(dz);
+      b.release(mrows[j - 1]);
+      dz = dx;
+    }
+    // first MLP layer: gradients w.r.t. the h and agg columns of [node | h | agg]
+    std::vector<int> dh = b.take(F), da = b.take(F);
+    add_bwd(S, dz, iota(Dn, 2 * F), cat({dh, da}), {});
+    b.release(dz);
+    b.release(a[S - 1]);
+    b.release(h[S - 1]);
+    {
+      FusedOp* ag = b.add_op();                                   // dh += Agg^T(da)   (last stage is linear: no gate)
+      ag->type = FOP_AGG; ag->transposed = 1; ag->in_tab = b.tab_put(da); ag->K = F;
+      ag->add_tab = b.tab_put(dh); ag->out_tab = ag->add_tab; ag->O = F;
+    }
+    b.release(da);
+    for (int st = S - 1; st >= 1; --st) {
+      std::vector<int> dxh = b.take(F), dxa = b.take(F);
+      std::vector<int> kk = cat({iota(0, F), iota(F + Dn + De, F)});
+      add_bwd(st, dh, kk, cat({dxh, dxa}), {});
+      b.release(dh);
+      b.release(a[st - 1]);
+      FusedOp* ag = b.add_op();                                   // dh(st-1) = relu'(h(st-1)) * (dxh + Agg^T(dxa))
+      ag->type = FOP_AGG; ag->transposed = 1; ag->in_tab = b.tab_put(dxa); ag->K = F;
+      ag->add_tab = b.tab_put(dxh); ag->out_tab = ag->add_tab; ag->O = F;
+      ag->gate_tab = b.tab_put(h[st - 1]);
+      b.release(dxa);
+      b.release(h[st - 1]);
+      dh = dxh;
+    }
+    add_bwd(0, dh, {}, {}, {});
+    P->n_blocks = blk;
+    P->n_bias = bias;
+  }
+  P->n_rows = b.next_row;
+  V2V_REQUIRE(!b.overflow, "fused path: program tables overflow");
+  return 0;
+}
+
+size_t fused_smem_bytes(const FusedProgram& p) {
+  size_t words = 0;
+  words += (p.n_params + 3) & ~3;
+  words += (p.n_tab + 3) & ~3;
+  words += (size_t)p.n_ops * (sizeof(FusedOp) / 4);
+  words += (p.TG * p.N + 3) & ~3;
+  words += 32;
+  words += (size_t)p.n_rows * p.RP;
+  return words * 4;
+}
+
+int fused_pick_tg(const FusedShape& s, int B, int train) {
+  // largest tile that fits shared memory, then the TG that minimises the per-SM critical path
+  FusedProgram* tmp = new FusedProgram();
+  int fit = 0;
+  for (int tg = 1; tg <= 64; ++tg) {
+    if (fused_build_program(s, tg, train, tmp) != 0) break;
+    if (fused_smem_bytes(*tmp) > 226 * 1024) break;
+    fit = tg;
+  }
+  delete tmp;
+  if (fit == 0) return 0;
+  const int sms = sm_count();
+  int best = 1;
+  double best_cost = 1e30;
+  for (int tg = 1; tg <= fit; ++tg) {
+    const int tiles = ceil_div(B, tg);
+    const int rounds = ceil_div(tiles, sms);
+    const int rp = (tg * s.N + 3) & ~3;
+    const double cost = rounds * (rp + 24.0);        // rows per tile + fixed per-tile overhead (barriers, loads)
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = tg; }
+  }
+  return best;
+}
+
+int fused_grid(const FusedProgram& p, int B) { return std::max(1, std::min(ceil_div(B, p.TG), sm_count())); }
+
+template <int NMAX>
+static int fused_launch_t(const FusedProgram& ph, const FusedProgram* prog_dev, const float* params, const float* node,
+                          const float* edge, const uint32_t* in_mask, const float* y, float* q_out, float* partial_dev,
+                          float* head_loss, int B, int grid, cudaStream_t st) {
+  const size_t smem = fused_smem_bytes(ph);
+  const float inv_cnt = 1.f / ((float)B * (float)ph.CH);
+  static size_t smem_set = 0;                  // per instantiation (NMAX): every kernel needs its own opt-in
+  if (smem > smem_set) {
+    V2V_CHECK_CUDA(cudaFuncSetAttribute(fused_brain_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  fused_brain_kernel<NMAX><<<grid, kFusedThreads, smem, st>>>(prog_dev, params, node, edge, in_mask, y, q_out, partial_dev,
+                                                              head_loss, B, inv_cnt);
+  return launch_status("fused_brain_kernel");
+}
+
+int fused_launch(const FusedProgram& ph, const FusedProgram* prog_dev, const float* params, const float* node,
+                 const float* edge, const uint32_t* in_mask, const float* y, float* q_out, float* partial_dev,
+                 float* head_loss, int B, int grid, cudaStream_t st) {
+#define V2V_FUSED_ARGS ph, prog_dev, params, node, edge, in_mask, y, q_out, partial_dev, head_loss, B, grid, st
+  if (ph.N <= 4) return fused_launch_t<4>(V2V_FUSED_ARGS);
+  if (ph.N <= 8) return fused_launch_t<8>(V2V_FUSED_ARGS);
+  if (ph.N <= 20) return fused_launch_t<20>(V2V_FUSED_ARGS);
+  return fused_launch_t<32>(V2V_FUSED_ARGS);
+#undef V2V_FUSED_ARGS
+}
+
+int fused_reduce_adam(const float* partial, int n_cta, float* grad, float* p, float* m, float* v, long n, int t, float lr,
+                      float b1, float b2, float eps, float gscale, cudaStream_t st) {
+  double lr_t = 0.0;
+  if (t >= 1) lr_t = (double)lr * (sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
+  const int threads = 128;
+  reduce_adam_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(partial, n_cta, grad, p, m, v, n, t >= 1,
+                                                                                 (float)lr_t, b1, b2, eps, gscale);
+  return launch_status("reduce_adam_kernel");
+}
+
+}  // namespace v2v

@@ -1,0 +1,83 @@
+// Whole-network fused kernel: shared declarations (see fused.cu).
+#pragma once
+#include "v2v_common.cuh"
+
+namespace v2v {
+
+enum FusedOpType : int {
+  FOP_GEMM = 0,    // out[o][r] = act(bias[o] + sum_k W[k][o] * in[k][r])
+  FOP_AGG = 1,     // out[f][g,m] = (add) + sum_n A[g][n][m] in[f][g,n]       (transposed = 1: roles of n, m swapped)
+  FOP_LOSS = 2,    // dq in place over q, per-head Huber sums
+  FOP_BWD = 3,     // weight-gradient blocks of one layer + its data gradient, one phase
+};
+
+// One step of the per-tile program.  All tensors live in a feature-major shared-memory arena
+// arena[feature_row][RP]; a tensor is a list of feature rows kept in the `tab` array, so that
+// concatenations (BS_brain.py:154-175) and in-place reuse of dead rows cost nothing.
+struct FusedOp {
+  int type;
+  int in_tab, K;          // GEMM/BWD: input rows (K of them); AGG: input rows (F)
+  int out_tab, O;         // GEMM: output rows (O); AGG: output rows (F)
+  int w_off, b_off;       // parameter offsets (floats) of W[K_ld][O] and bias[O]
+  int relu;               // GEMM: relu epilogue
+  int add_tab;            // AGG: rows added to the result (-1: none)
+  int gate_tab;           // AGG: relu gate rows for the result (-1); BWD: gate rows of the dx outputs (-1)
+  int transposed;         // AGG
+  int dz_tab;             // BWD: dz rows (O)
+  int dxk_tab, dx_tab, n_dx;   // BWD: weight-row index of every requested dx column, its output rows, count (multiple of 4)
+  int blk0, nblk;         // BWD: range of global weight-gradient block ids of this layer
+  int bias0;              // BWD: first global bias-gradient slot of this layer
+  int pad_[2];            // keep sizeof(FusedOp) a multiple of 16 bytes (shared-memory carve-up alignment)
+};
+static_assert(sizeof(FusedOp) % 16 == 0, "FusedOp must stay 16-byte sized");
+
+constexpr int kFusedMaxOps = 48;
+constexpr int kFusedMaxTab = 3072;
+constexpr int kFusedThreads = 384;
+constexpr int kFusedBlkPerThread = 2;
+
+struct FusedProgram {
+  int n_ops;
+  int n_tab;
+  int n_rows;             // arena feature rows
+  int zero_row;           // an all-zero feature row
+  int x0_row0, Dn, De;    // input rows: node features then edge features, contiguous from x0_row0
+  int q_tab, y_tab;       // Q rows / target rows (CH each)
+  int N, TG, R, RP, CH, F;
+  int n_params;
+  int n_blocks;           // weight-gradient 4x4 blocks over all layers
+  int n_bias;             // bias-gradient slots over all layers
+  int train;              // 1: loss + backward, 0: forward only
+  FusedOp ops[kFusedMaxOps];
+  int tab[kFusedMaxTab];
+  // block b -> op index, k0, o0 (packed: op<<16 | k0<<8 | o0), bias slot -> op<<16 | o
+  int blk_info[kFusedThreads * kFusedBlkPerThread];
+  int bias_info[kFusedThreads];
+};
+
+// Build the program for a brain configuration.  Returns 0 on success, non-zero (with last_error) if
+// the configuration is outside the fused path (then the layered kernels are used).
+struct FusedShape {
+  int N, Dn, De, F, CH, S, H1, H2, H3;
+  const int* layer_K;      // stacked weight rows per layer
+  const int* layer_O;
+  const size_t* w_off;
+  const size_t* b_off;
+  int n_layers;
+  size_t n_params;
+};
+int fused_build_program(const FusedShape& s, int TG, int train, FusedProgram* out);
+size_t fused_smem_bytes(const FusedProgram& p);
+int fused_pick_tg(const FusedShape& s, int B, int train);
+
+// Launch.  prog_dev: the program in device memory.  partial_dev: [grid][n_params] per-CTA gradient partials.
+int fused_launch(const FusedProgram& prog_host, const FusedProgram* prog_dev, const float* params, const float* node,
+                 const float* edge, const uint32_t* in_mask, const float* y, float* q_out, float* partial_dev,
+                 float* head_loss, int B, int grid, cudaStream_t st);
+int fused_grid(const FusedProgram& p, int B);
+
+// grad[i] = sum_c partial[c][i]; optional Keras-Adam in the same pass (t >= 1).
+int fused_reduce_adam(const float* partial, int n_cta, float* grad, float* p, float* m, float* v, long n, int t, float lr,
+                      float b1, float b2, float eps, float gscale, cudaStream_t st);
+
+}  // namespace v2v

@@ -163,6 +163,15 @@ long v2v_brain_param_count(const v2v_brain* b);
 int v2v_brain_get_params(v2v_brain* b, int which, float* host_out, void* stream);
 int v2v_brain_set_params(v2v_brain* b, int which, const float* host_in, void* stream);
 float* v2v_brain_param_ptr(v2v_brain* b, int which);     /* device pointer */
+/* The shared-weight brain (per_slot = 0, N <= 32, binary adjacency, zero neighbour input) runs
+ * forward/backward as ONE fused kernel per call; enable = 0 forces the layer-by-layer kernels
+ * (what per-slot weights, weighted adjacency or N > 32 always use).  Default: enabled. */
+int v2v_brain_set_fused(v2v_brain* b, int enable);
+/* Describes the fused program for a batch of B graphs: info8 = {capable, graphs per tile, arena
+ * feature rows, shared-memory bytes, phases, weight-gradient blocks, bias slots, table entries}. */
+int v2v_brain_fused_info(v2v_brain* b, int B, int train, int* info8);
+/* Same query from a configuration alone (host-only, no device needed). */
+int v2v_fused_plan(const v2v_brain_config* cfg, int B, int train, int* info8);
 /* update_target_model (BS_brain.py:237-239) */
 int v2v_brain_update_target(v2v_brain* b, void* stream);
 int v2v_brain_get_iterations(const v2v_brain* b);
