@@ -259,6 +259,8 @@ extern "C" int v2v_brain_set_params(v2v_brain* b, int which, const float* host_i
   return 0;
 }
 
+extern "C" int v2v_fused_set_trace(long long* dev_buf) { return fused_set_trace(dev_buf); }
+
 extern "C" int v2v_brain_set_fused(v2v_brain* b, int enable) {
   V2V_REQUIRE(b, "v2v_brain_set_fused: null brain");
   b->fused_enabled = enable != 0;
@@ -375,8 +377,8 @@ extern "C" int v2v_brain_forward(v2v_brain* b, const float* node_dev, const floa
   if (use_fused(b, in_mask_dev, neighbor_dev)) {
     v2v_brain::FusedEntry* e = nullptr;
     if (int rc = fused_get(b, B, 0, &e)) return rc;
-    return fused_launch(e->host, e->dev, b->params[target ? 1 : 0], node_dev, edge_dev, in_mask_dev, nullptr, q_dev, nullptr,
-                        nullptr, B, fused_grid(e->host, B), (cudaStream_t)stream);
+    return fused_launch(e->host, e->dev, b->params[target ? 1 : 0], node_dev, edge_dev, in_mask_dev, nullptr, nullptr, q_dev,
+                        nullptr, nullptr, B, fused_grid(e->host, B), (cudaStream_t)stream);
   }
   return forward_impl(b, b->params[target ? 1 : 0], node_dev, edge_dev, neighbor_dev, in_mask_dev, adj_dev, B, q_dev, stream);
 }
@@ -404,7 +406,7 @@ extern "C" int v2v_brain_forward_backward(v2v_brain* b, const float* node, const
     V2V_CHECK_CUDA(cudaMemsetAsync(hl, 0, N * sizeof(float), st));
     const int grid = fused_grid(e->host, B);
     b->last_grid = grid;
-    if (int rc = fused_launch(e->host, e->dev, P, node, edge, im, y, nullptr, b->partial, hl, B, grid, st)) return rc;
+    if (int rc = fused_launch(e->host, e->dev, P, node, edge, im, om, y, nullptr, b->partial, hl, B, grid, st)) return rc;
     if (b->defer_reduce) return 0;      // train_step fuses the reduction with Adam
     return fused_reduce_adam(b->partial, grid, Gd, nullptr, nullptr, nullptr, (long)b->n_params, 0, 0.f, 0.f, 0.f, 0.f, 1.f, st);
   }

@@ -50,8 +50,10 @@ __device__ __forceinline__ void gemm_phase(const FusedOp& op, float* arena, cons
                                            int tid) {
   const int row_groups = RP / TR;
   const int items = row_groups * (op.O / TC);
-  const int* in_rows = tab + op.in_tab;
+  const int4* in_rows4 = reinterpret_cast<const int4*>(tab + op.in_tab);     // padded to a multiple of 4 with zero_row
   const int* out_rows = tab + op.out_tab;
+  const int K4 = (op.K + 3) >> 2;
+  const int O = op.O;
   for (int item = tid; item < items; item += kFusedThreads) {
     const int cg = item / row_groups, rg = item - cg * row_groups;
     const int r0 = rg * TR, o0 = cg * TC;
@@ -63,20 +65,26 @@ __device__ __forceinline__ void gemm_phase(const FusedOp& op, float* arena, cons
       for (int i = 0; i < TR; ++i) acc[j][i] = b;
     }
     const float* wp = Ws + op.w_off + o0;
-#pragma unroll 2
-    for (int k = 0; k < op.K; ++k) {
-      RowVec<TR> x;
-      x.load(arena + in_rows[k] * RP + r0);
-      float w[TC];
+    const float* xb = arena + r0;
+    for (int k4 = 0; k4 < K4; ++k4) {
+      const int4 rows = in_rows4[k4];
+      RowVec<TR> x[4];
+      x[0].load(xb + rows.x * RP); x[1].load(xb + rows.y * RP); x[2].load(xb + rows.z * RP); x[3].load(xb + rows.w * RP);
+      float w[4][TC];
 #pragma unroll
-      for (int j4 = 0; j4 < TC; j4 += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(wp + k * op.O + j4);
-        w[j4] = t.x; w[j4 + 1] = t.y; w[j4 + 2] = t.z; w[j4 + 3] = t.w;
-      }
+      for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
-      for (int j = 0; j < TC; ++j)
+        for (int j4 = 0; j4 < TC; j4 += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(wp + kk * O + j4);
+          w[kk][j4] = t.x; w[kk][j4 + 1] = t.y; w[kk][j4 + 2] = t.z; w[kk][j4 + 3] = t.w;
+        }
+      wp += 4 * O;
 #pragma unroll
-        for (int i = 0; i < TR; ++i) acc[j][i] = fmaf(x.v[i], w[j], acc[j][i]);
+      for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int j = 0; j < TC; ++j)
+#pragma unroll
+          for (int i = 0; i < TR; ++i) acc[j][i] = fmaf(x[kk].v[i], w[kk][j], acc[j][i]);
     }
 #pragma unroll
     for (int j = 0; j < TC; ++j) {
@@ -107,23 +115,15 @@ __device__ __forceinline__ void agg_phase(const FusedOp& op, float* arena, const
     float acc[MT];
 #pragma unroll
     for (int j = 0; j < MT; ++j) acc[j] = 0.f;
-    if (!op.transposed) {
+    // forward: in_mask[m] bit n = Adj[n][m]; transposed: out_mask[n] bit m = Adj[n][m] -- same gather-reduce
+    const uint32_t* mk = (op.transposed ? mask_s + TG * N : mask_s) + g * N;
 #pragma unroll
-      for (int j = 0; j < MT; ++j) {
-        const int m = ms + j * MS;
-        const uint32_t msk = (m < N) ? mask_s[g * N + m] : 0u;
+    for (int j = 0; j < MT; ++j) {
+      const int m = ms + j * MS;
+      const uint32_t msk = (m < N) ? mk[m] : 0u;
 #pragma unroll
-        for (int n = 0; n < NMAX; ++n)
-          if (msk & (1u << n)) acc[j] += v[n];
-      }
-    } else {
-#pragma unroll
-      for (int m = 0; m < NMAX; ++m) {
-        const uint32_t msk = (m < N) ? mask_s[g * N + m] : 0u;
-#pragma unroll
-        for (int j = 0; j < MT; ++j)
-          if (msk & (1u << ((ms + j * MS) & 31))) acc[j] += v[m];
-      }
+      for (int n = 0; n < NMAX; ++n)
+        if (msk & (1u << n)) acc[j] += v[n];
     }
     float* dst = arena + tab[op.out_tab + f] * RP + g * N;
     const float* add = op.add_tab >= 0 ? arena + tab[op.add_tab + f] * RP + g * N : nullptr;
@@ -169,13 +169,14 @@ __device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* 
     const int b = tid + s * kFusedThreads;
     if (b >= op.blk0 && b < op.blk0 + op.nblk) {
       const int kb = (my_blk[s] >> 8) & 0xff, ob = my_blk[s] & 0xff;
+      const int OB = op.O >> 2;
       const float* xr[4];
       const float* dr[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int k = kb * 4 + i;
         xr[i] = arena + (k < op.K ? tab[op.in_tab + k] : zero_row) * RP;
-        dr[i] = arena + tab[op.dz_tab + ob * 4 + i] * RP;
+        dr[i] = arena + tab[op.dz_tab + ob + i * OB] * RP;      // strided columns: lanes hit consecutive rows
       }
       float a[16];
 #pragma unroll
@@ -224,10 +225,13 @@ __device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* 
       float4 acc[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int4* dz_rows4 = reinterpret_cast<const int4*>(tab + op.dz_tab);
+      const float* ab = arena + r0;
       for (int o = 0; o < op.O; o += 4) {
+        const int4 zr = dz_rows4[o >> 2];
         float4 dz[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dz[j] = *reinterpret_cast<const float4*>(arena + tab[op.dz_tab + o + j] * RP + r0);
+        dz[0] = *reinterpret_cast<const float4*>(ab + zr.x * RP); dz[1] = *reinterpret_cast<const float4*>(ab + zr.y * RP);
+        dz[2] = *reinterpret_cast<const float4*>(ab + zr.z * RP); dz[3] = *reinterpret_cast<const float4*>(ab + zr.w * RP);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float4 w = *reinterpret_cast<const float4*>(wr[i] + o);
@@ -255,11 +259,13 @@ __device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* 
   }
 }
 
+__device__ long long* g_fused_trace = nullptr;       // optional per-phase clock trace of CTA 0 (profiling aid)
+
 template <int NMAX>
 __global__ void __launch_bounds__(kFusedThreads, 1)
 fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__ params, const float* __restrict__ node,
-                   const float* __restrict__ edge, const uint32_t* __restrict__ in_mask, const float* __restrict__ y,
-                   float* __restrict__ q_out, float* __restrict__ partial, float* __restrict__ head_loss, int B,
+                   const float* __restrict__ edge, const uint32_t* __restrict__ in_mask,
+                   const uint32_t* __restrict__ out_mask, const float* __restrict__ y, float* __restrict__ q_out, float* __restrict__ partial, float* __restrict__ head_loss, int B,
                    float inv_cnt) {
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x;
@@ -270,7 +276,7 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
   int* tab = reinterpret_cast<int*>(Ws + np_pad);
   FusedOp* ops = reinterpret_cast<FusedOp*>(tab + ((n_tab + 3) & ~3));
   uint32_t* mask_s = reinterpret_cast<uint32_t*>(ops + n_ops);
-  float* hl_s = reinterpret_cast<float*>(mask_s + ((TG * N + 3) & ~3));
+  float* hl_s = reinterpret_cast<float*>(mask_s + ((2 * TG * N + 3) & ~3));
   float* arena = hl_s + 32;
 
   for (int i = tid; i < n_params / 4; i += kFusedThreads)
@@ -316,8 +322,10 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
         const int r = idx / De, f = idx - r * De;
         arena[(P->x0_row0 + Dn + f) * RP + r] = (r < valid_rows) ? esrc[idx] : 0.f;
       }
-      for (int idx = tid; idx < TG * N; idx += kFusedThreads)
+      for (int idx = tid; idx < TG * N; idx += kFusedThreads) {
         mask_s[idx] = (idx < valid_rows) ? in_mask[(size_t)g0 * N + idx] : 0u;
+        if (train) mask_s[TG * N + idx] = (idx < valid_rows) ? out_mask[(size_t)g0 * N + idx] : 0u;
+      }
       if (train) {
         const float* ysrc = y + (size_t)g0 * N * CH;
         for (int idx = tid; idx < RP * CH; idx += kFusedThreads) {
@@ -327,6 +335,8 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
       }
     }
     __syncthreads();
+    long long* trace = (blockIdx.x == 0 && tid == kFusedThreads - 1 && tile == 0) ? g_fused_trace : nullptr;
+    if (trace) trace[0] = clock64();
     for (int oi = 0; oi < n_ops; ++oi) {
       const FusedOp& op = ops[oi];
       switch (op.type) {
@@ -343,6 +353,7 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
         default: break;
       }
       __syncthreads();
+      if (trace) trace[oi + 1] = clock64();
     }
     if (!train) {
       float* qdst = q_out + (size_t)g0 * N * CH;
@@ -362,11 +373,13 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
         const FusedOp& op = ops[my_blk[s] >> 16];
         const int kb = (my_blk[s] >> 8) & 0xff, ob = my_blk[s] & 0xff;
 #pragma unroll
+        const int OB = op.O >> 2;
         for (int i = 0; i < 4; ++i) {
           const int k = kb * 4 + i;
-          if (k < op.K)
-            *reinterpret_cast<float4*>(dst + op.w_off + k * op.O + ob * 4) =
-                make_float4(wacc[s][i * 4], wacc[s][i * 4 + 1], wacc[s][i * 4 + 2], wacc[s][i * 4 + 3]);
+          if (k < op.K) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[op.w_off + k * op.O + ob + j * OB] = wacc[s][i * 4 + j];
+          }
         }
       }
     }
@@ -413,10 +426,12 @@ struct Builder {
   int next_row = 0;
   bool overflow = false;
 
-  int tab_put(const std::vector<int>& rows) {
+  int tab_put(const std::vector<int>& rows) {          // 16-B aligned, padded to a multiple of 4 with the zero row
     const int off = P->n_tab;
-    if (off + (int)rows.size() > kFusedMaxTab) { overflow = true; return 0; }
+    const int n = ((int)rows.size() + 3) & ~3;
+    if (off + n > kFusedMaxTab) { overflow = true; return 0; }
     for (int r : rows) P->tab[P->n_tab++] = r;
+    while (P->n_tab < off + n) P->tab[P->n_tab++] = P->zero_row;
     return off;
   }
   std::vector<int> fresh(int n) {
@@ -580,7 +595,7 @@ size_t fused_smem_bytes(const FusedProgram& p) {
   words += (p.n_params + 3) & ~3;
   words += (p.n_tab + 3) & ~3;
   words += (size_t)p.n_ops * (sizeof(FusedOp) / 4);
-  words += (p.TG * p.N + 3) & ~3;
+  words += (2 * p.TG * p.N + 3) & ~3;
   words += 32;
   words += (size_t)p.n_rows * p.RP;
   return words * 4;
@@ -614,8 +629,8 @@ int fused_grid(const FusedProgram& p, int B) { return std::max(1, std::min(ceil_
 
 template <int NMAX>
 static int fused_launch_t(const FusedProgram& ph, const FusedProgram* prog_dev, const float* params, const float* node,
-                          const float* edge, const uint32_t* in_mask, const float* y, float* q_out, float* partial_dev,
-                          float* head_loss, int B, int grid, cudaStream_t st) {
+                          const float* edge, const uint32_t* in_mask, const uint32_t* out_mask, const float* y, float* q_out,
+                          float* partial_dev, float* head_loss, int B, int grid, cudaStream_t st) {
   const size_t smem = fused_smem_bytes(ph);
   const float inv_cnt = 1.f / ((float)B * (float)ph.CH);
   static size_t smem_set = 0;                  // per instantiation (NMAX): every kernel needs its own opt-in
@@ -623,20 +638,25 @@ static int fused_launch_t(const FusedProgram& ph, const FusedProgram* prog_dev, 
     V2V_CHECK_CUDA(cudaFuncSetAttribute(fused_brain_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  fused_brain_kernel<NMAX><<<grid, kFusedThreads, smem, st>>>(prog_dev, params, node, edge, in_mask, y, q_out, partial_dev,
-                                                              head_loss, B, inv_cnt);
+  fused_brain_kernel<NMAX><<<grid, kFusedThreads, smem, st>>>(prog_dev, params, node, edge, in_mask, out_mask, y, q_out,
+                                                              partial_dev, head_loss, B, inv_cnt);
   return launch_status("fused_brain_kernel");
 }
 
 int fused_launch(const FusedProgram& ph, const FusedProgram* prog_dev, const float* params, const float* node,
-                 const float* edge, const uint32_t* in_mask, const float* y, float* q_out, float* partial_dev,
-                 float* head_loss, int B, int grid, cudaStream_t st) {
-#define V2V_FUSED_ARGS ph, prog_dev, params, node, edge, in_mask, y, q_out, partial_dev, head_loss, B, grid, st
+                 const float* edge, const uint32_t* in_mask, const uint32_t* out_mask, const float* y, float* q_out,
+                 float* partial_dev, float* head_loss, int B, int grid, cudaStream_t st) {
+#define V2V_FUSED_ARGS ph, prog_dev, params, node, edge, in_mask, out_mask, y, q_out, partial_dev, head_loss, B, grid, st
   if (ph.N <= 4) return fused_launch_t<4>(V2V_FUSED_ARGS);
   if (ph.N <= 8) return fused_launch_t<8>(V2V_FUSED_ARGS);
   if (ph.N <= 20) return fused_launch_t<20>(V2V_FUSED_ARGS);
   return fused_launch_t<32>(V2V_FUSED_ARGS);
 #undef V2V_FUSED_ARGS
+}
+
+int fused_set_trace(long long* dev_buf) {
+  V2V_CHECK_CUDA(cudaMemcpyToSymbol(g_fused_trace, &dev_buf, sizeof(dev_buf)));
+  return 0;
 }
 
 int fused_reduce_adam(const float* partial, int n_cta, float* grad, float* p, float* m, float* v, long n, int t, float lr,

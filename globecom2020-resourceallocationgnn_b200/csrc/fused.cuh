@@ -72,9 +72,10 @@ int fused_pick_tg(const FusedShape& s, int B, int train);
 
 // Launch.  prog_dev: the program in device memory.  partial_dev: [grid][n_params] per-CTA gradient partials.
 int fused_launch(const FusedProgram& prog_host, const FusedProgram* prog_dev, const float* params, const float* node,
-                 const float* edge, const uint32_t* in_mask, const float* y, float* q_out, float* partial_dev,
-                 float* head_loss, int B, int grid, cudaStream_t st);
+                 const float* edge, const uint32_t* in_mask, const uint32_t* out_mask, const float* y, float* q_out,
+                 float* partial_dev, float* head_loss, int B, int grid, cudaStream_t st);
 int fused_grid(const FusedProgram& p, int B);
+int fused_set_trace(long long* dev_buf);      // dev_buf: >= kFusedMaxOps + 1 entries, or nullptr to disable
 
 // grad[i] = sum_c partial[c][i]; optional Keras-Adam in the same pass (t >= 1).
 int fused_reduce_adam(const float* partial, int n_cta, float* grad, float* p, float* m, float* v, long n, int t, float lr,
