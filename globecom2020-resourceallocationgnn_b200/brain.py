@@ -141,8 +141,8 @@ class BS:
         self.param_count = int(self._lib.v2v_brain_param_count(h))
         self._views = [torch.as_tensor(_DevBuf(self._lib.v2v_brain_param_ptr(h, w), self.param_count), device=self._dev)
                        for w in range(5)]
-        if not getattr(self, "_fused", True):
-            _lib.check(self._lib.v2v_brain_set_fused(h, 0))
+        if getattr(self, "_fused", 1) != 1:
+            _lib.check(self._lib.v2v_brain_set_fused(h, int(self._fused)))
         if keep_state is not None:
             for w, t in enumerate(keep_state["bufs"]):
                 self._views[w].copy_(t)
@@ -260,11 +260,12 @@ class BS:
             chunks += [W.ravel(), b.ravel()]
         self.set_flat_params(np.concatenate(chunks), which)
 
-    def set_fused(self, enable: bool):
+    def set_fused(self, enable):
         """Shared-weight brains run forward/backward as one fused kernel; ``False`` forces the
         layer-by-layer kernels (always used for per-slot weights, weighted adjacency, N > 32)."""
-        _lib.check(self._lib.v2v_brain_set_fused(self._handle, int(bool(enable))))
-        self._fused = bool(enable)
+        mode = int(bool(enable))
+        _lib.check(self._lib.v2v_brain_set_fused(self._handle, mode))
+        self._fused = mode
 
     def fused_info(self, B, train=True):
         info = (C.c_int * 8)()

@@ -66,6 +66,7 @@ __device__ __forceinline__ void gemm_phase(const FusedOp& op, float* arena, cons
     }
     const float* wp = Ws + op.w_off + o0;
     const float* xb = arena + r0;
+#pragma unroll 2
     for (int k4 = 0; k4 < K4; ++k4) {
       const int4 rows = in_rows4[k4];
       RowVec<TR> x[4];
@@ -125,6 +126,8 @@ __device__ __forceinline__ void agg_phase(const FusedOp& op, float* arena, const
       for (int n = 0; n < NMAX; ++n)
         if (msk & (1u << n)) acc[j] += v[n];
     }
+    if (g == 0 && ms == 0)                                  // rows past the tile's last node: exact zeros
+      for (int r = TG * N; r < RP; ++r) arena[tab[op.out_tab + f] * RP + r] = 0.f;
     float* dst = arena + tab[op.out_tab + f] * RP + g * N;
     const float* add = op.add_tab >= 0 ? arena + tab[op.add_tab + f] * RP + g * N : nullptr;
     const float* gate = op.gate_tab >= 0 ? arena + tab[op.gate_tab + f] * RP + g * N : nullptr;
@@ -140,6 +143,7 @@ __device__ __forceinline__ void agg_phase(const FusedOp& op, float* arena, const
     }
   }
 }
+
 
 __device__ __forceinline__ void loss_phase(const FusedProgram* P, float* arena, const int* tab, float* hl_s, int RP,
                                            int valid_rows, float inv_cnt, int tid) {
@@ -160,49 +164,8 @@ __device__ __forceinline__ void loss_phase(const FusedProgram* P, float* arena, 
   }
 }
 
-__device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* arena, const float* Ws, const int* tab, int RP,
-                                          int zero_row, int tid, const int (&my_blk)[kFusedBlkPerThread],
-                                          float (&wacc)[kFusedBlkPerThread][16], int my_bias, float& bacc) {
-  // ---- weight-gradient blocks owned by this thread that belong to this layer
-#pragma unroll
-  for (int s = 0; s < kFusedBlkPerThread; ++s) {
-    const int b = tid + s * kFusedThreads;
-    if (b >= op.blk0 && b < op.blk0 + op.nblk) {
-      const int kb = (my_blk[s] >> 8) & 0xff, ob = my_blk[s] & 0xff;
-      const int OB = op.O >> 2;
-      const float* xr[4];
-      const float* dr[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int k = kb * 4 + i;
-        xr[i] = arena + (k < op.K ? tab[op.in_tab + k] : zero_row) * RP;
-        dr[i] = arena + tab[op.dz_tab + ob + i * OB] * RP;      // strided columns: lanes hit consecutive rows
-      }
-      float a[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) a[i] = 0.f;
-      for (int r = 0; r < RP; r += 4) {
-        float4 xv[4], dv[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          xv[i] = *reinterpret_cast<const float4*>(xr[i] + r);
-          dv[i] = *reinterpret_cast<const float4*>(dr[i] + r);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float t = a[i * 4 + j];
-            t = fmaf(xv[i].x, dv[j].x, t); t = fmaf(xv[i].y, dv[j].y, t);
-            t = fmaf(xv[i].z, dv[j].z, t); t = fmaf(xv[i].w, dv[j].w, t);
-            a[i * 4 + j] = t;
-          }
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) wacc[s][i] += a[i];
-    }
-  }
-  // ---- bias gradient slot
+__device__ __forceinline__ void bias_grad(const FusedOp& op, int op_idx, const float* arena, const int* tab, int RP,
+                                          int my_bias, float& bacc) {
   if (my_bias >= 0 && (my_bias >> 16) == op_idx) {
     const float* dz = arena + tab[op.dz_tab + (my_bias & 0xffff)] * RP;
     float s = 0.f;
@@ -212,11 +175,100 @@ __device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* 
     }
     bacc += s;
   }
+}
+
+// 4x4 weight-gradient block: a[i*4+j] += sum over rows r = r_begin, r_begin + r_step, ... (4 rows each)
+__device__ __forceinline__ void wgrad_block(const FusedOp& op, const float* arena, const int* tab, int RP, int zero_row,
+                                            int kb, int ob, int r_begin, int r_step, float (&a)[16]) {
+  const int OB = op.O >> 2;
+  const float* xr[4];
+  const float* dr[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = kb * 4 + i;
+    xr[i] = arena + (k < op.K ? tab[op.in_tab + k] : zero_row) * RP;
+    dr[i] = arena + tab[op.dz_tab + ob + i * OB] * RP;      // strided columns: the lanes of a warp hit consecutive rows
+  }
+#pragma unroll 2
+  for (int r = r_begin; r < RP; r += r_step) {
+    float4 xv[4], dv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      xv[i] = *reinterpret_cast<const float4*>(xr[i] + r);
+      dv[i] = *reinterpret_cast<const float4*>(dr[i] + r);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float t = a[i * 4 + j];
+        t = fmaf(xv[i].x, dv[j].x, t); t = fmaf(xv[i].y, dv[j].y, t);
+        t = fmaf(xv[i].z, dv[j].z, t); t = fmaf(xv[i].w, dv[j].w, t);
+        a[i * 4 + j] = t;
+      }
+  }
+}
+
+__device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* arena, const float* Ws, const int* tab, int RP,
+                                          int zero_row, int tid, const int (&my_blk)[kFusedBlkPerThread],
+                                          float (&wacc)[kFusedBlkPerThread][16], int my_bias, float& bacc, float* dWs) {
+  // ---- weight gradient.  Large layers: 4x4 blocks owned by fixed threads, accumulated in registers across
+  // tiles.  Small layers (op.nwt = RS > 0): every block is split over RS adjacent lanes by row groups, reduced
+  // with shuffles, and the first lane adds the block into the CTA's shared accumulator (one owner per
+  // address: deterministic) -- otherwise a 5..48-block layer would leave most of the CTA idle.
+  int owners_begin, owners_n;
+  if (op.nwt > 0) {
+    const int RS = op.nwt, OB = op.O >> 2;
+    const int tasks = op.nblk * RS;
+    const int blk = tid / RS, split = tid - blk * RS;
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = 0.f;
+    const int kb = blk / OB, ob = blk - kb * OB;
+    if (tid < tasks) wgrad_block(op, arena, tab, RP, zero_row, kb, ob, split * 4, RS * 4, a);
+    for (int off = RS >> 1; off > 0; off >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], off);
+    }
+    if (tid < tasks && split == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = kb * 4 + i;
+        if (k < op.K) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dWs[op.wt0 + k * op.O + ob + j * OB] += a[i * 4 + j];
+        }
+      }
+    }
+    owners_begin = 0;
+    owners_n = min(tasks, kFusedThreads);
+  } else {
+#pragma unroll
+    for (int s = 0; s < kFusedBlkPerThread; ++s) {
+      const int b = tid + s * kFusedThreads;
+      if (b >= op.blk0 && b < op.blk0 + op.nblk) {
+        float a[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = 0.f;
+        wgrad_block(op, arena, tab, RP, zero_row, (my_blk[s] >> 8) & 0xff, my_blk[s] & 0xff, 0, 4, a);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) wacc[s][i] += a[i];
+      }
+    }
+    owners_begin = op.blk0 % kFusedThreads;
+    owners_n = min(op.nblk, kFusedThreads);
+  }
+  bias_grad(op, op_idx, arena, tab, RP, my_bias, bacc);
   // ---- data gradient of the requested input columns (4 rows x 4 columns per item)
   if (op.n_dx > 0) {
     const int row_groups = RP / 4;
     const int items = row_groups * (op.n_dx / 4);
-    for (int item = kFusedThreads - 1 - tid; item < items; item += kFusedThreads) {
+    // hand the items to the threads that had no weight-gradient work in this phase (cyclic owner range)
+    int rank = (tid - owners_begin - owners_n) % kFusedThreads;      // owner range may wrap around the CTA
+    if (rank < 0) rank += kFusedThreads;
+    int workers = kFusedThreads - owners_n;
+    if (workers < 96) { rank = kFusedThreads - 1 - tid; workers = kFusedThreads; }
+    for (int item = (rank < workers ? rank : items); item < items; item += workers) {
       const int kg = item / row_groups, rg = item - kg * row_groups;
       const int r0 = rg * 4;
       const float* wr[4];
@@ -227,6 +279,7 @@ __device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* 
       for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       const int4* dz_rows4 = reinterpret_cast<const int4*>(tab + op.dz_tab);
       const float* ab = arena + r0;
+#pragma unroll 2
       for (int o = 0; o < op.O; o += 4) {
         const int4 zr = dz_rows4[o >> 2];
         float4 dz[4];
@@ -277,7 +330,8 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
   FusedOp* ops = reinterpret_cast<FusedOp*>(tab + ((n_tab + 3) & ~3));
   uint32_t* mask_s = reinterpret_cast<uint32_t*>(ops + n_ops);
   float* hl_s = reinterpret_cast<float*>(mask_s + ((2 * TG * N + 3) & ~3));
-  float* arena = hl_s + 32;
+  float* dWs = hl_s + 32;                                   // shared weight-gradient accumulator of the small layers
+  float* arena = dWs + P->n_small;
 
   for (int i = tid; i < n_params / 4; i += kFusedThreads)
     reinterpret_cast<float4*>(Ws)[i] = reinterpret_cast<const float4*>(params)[i];
@@ -290,10 +344,13 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
     for (int i = tid; i < words; i += kFusedThreads) dst[i] = src[i];
   }
   if (tid < 32) hl_s[tid] = 0.f;
-  for (int i = tid; i < RP; i += kFusedThreads) arena[P->zero_row * RP + i] = 0.f;
+  for (int i = tid; i < P->n_small; i += kFusedThreads) dWs[i] = 0.f;
+  for (int i = tid; i < P->n_rows * RP / 4; i += kFusedThreads)      // whole arena: finite everywhere, zero row included
+    reinterpret_cast<float4*>(arena)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
+  const int warp = tid >> 5, lane = tid & 31;
   int my_blk[kFusedBlkPerThread];
-  float wacc[kFusedBlkPerThread][16];
+  float wacc[kFusedBlkPerThread][16];                  // two 4x4 weight-gradient blocks per thread (large layers)
 #pragma unroll
   for (int s = 0; s < kFusedBlkPerThread; ++s) {
     const int b = tid + s * kFusedThreads;
@@ -335,8 +392,9 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
       }
     }
     __syncthreads();
-    long long* trace = (blockIdx.x == 0 && tid == kFusedThreads - 1 && tile == 0) ? g_fused_trace : nullptr;
-    if (trace) trace[0] = clock64();
+    // profiling aid: lane 0 of every warp of CTA 0 records [phase][warp] = {work done, barrier released}
+    long long* trace = (blockIdx.x == 0 && lane == 0 && tile == 0) ? g_fused_trace : nullptr;
+    if (trace) trace[warp * 2 + 1] = clock64();
     for (int oi = 0; oi < n_ops; ++oi) {
       const FusedOp& op = ops[oi];
       switch (op.type) {
@@ -349,11 +407,12 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
         }
         case FOP_AGG: agg_phase<NMAX>(op, arena, tab, mask_s, RP, N, TG, tid); break;
         case FOP_LOSS: loss_phase(P, arena, tab, hl_s, RP, valid_rows, inv_cnt, tid); break;
-        case FOP_BWD: bwd_phase(op, oi, arena, Ws, tab, RP, P->zero_row, tid, my_blk, wacc, my_bias, bacc); break;
+        case FOP_BWD: bwd_phase(op, oi, arena, Ws, tab, RP, P->zero_row, tid, my_blk, wacc, my_bias, bacc, dWs); break;
         default: break;
       }
+      if (trace) trace[((oi + 1) * kFusedWarps + warp) * 2] = clock64();
       __syncthreads();
-      if (trace) trace[oi + 1] = clock64();
+      if (trace) trace[((oi + 1) * kFusedWarps + warp) * 2 + 1] = clock64();
     }
     if (!train) {
       float* qdst = q_out + (size_t)g0 * N * CH;
@@ -384,6 +443,12 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
       }
     }
     if (my_bias >= 0) dst[ops[my_bias >> 16].b_off + (my_bias & 0xffff)] = bacc;
+    __syncthreads();
+    for (int oi = 0; oi < n_ops; ++oi) {
+      const FusedOp& op = ops[oi];
+      if (op.type == FOP_BWD && op.nwt > 0)
+        for (int i = tid; i < op.K * op.O; i += kFusedThreads) dst[op.w_off + i] = dWs[op.wt0 + i];
+    }
     __syncthreads();
     if (tid < N && hl_s[tid] != 0.f) atomicAdd(&head_loss[tid], hl_s[tid] * inv_cnt);
   }
@@ -426,7 +491,7 @@ struct Builder {
   int next_row = 0;
   bool overflow = false;
 
-  int tab_put(const std::vector<int>& rows) {          // 16-B aligned, padded to a multiple of 4 with the zero row
+  int tab_put(const std::vector<int>& rows) {          // 16-B aligned, padded with the zero row
     const int off = P->n_tab;
     const int n = ((int)rows.size() + 3) & ~3;
     if (off + n > kFusedMaxTab) { overflow = true; return 0; }
@@ -534,7 +599,16 @@ int fused_build_program(const FusedShape& s, int TG, int train, FusedProgram* ou
       o->blk0 = blk;
       const int kb_n = (o->K + 3) / 4, ob_n = o->O / 4;
       o->nblk = kb_n * ob_n;
-      for (int kb = 0; kb < kb_n; ++kb)
+      const bool small = o->nblk <= 96;
+      if (small) {                 // row-split weight gradient into the shared accumulator (wt0 = offset, nwt = RS)
+        int rs = 1;
+        while (rs < 8 && o->nblk * rs * 2 <= kFusedThreads) rs *= 2;
+        o->wt0 = P->n_small;
+        o->nwt = rs;
+        P->n_small += (o->K * o->O + 3) & ~3;
+        o->blk0 = -1;
+      }
+      for (int kb = 0; kb < kb_n && !small; ++kb)
         for (int ob = 0; ob < ob_n; ++ob) {
           if (blk >= kFusedThreads * kFusedBlkPerThread) { b.overflow = true; break; }
           P->blk_info[blk++] = (op_idx << 16) | (kb << 8) | ob;
@@ -597,6 +671,7 @@ size_t fused_smem_bytes(const FusedProgram& p) {
   words += (size_t)p.n_ops * (sizeof(FusedOp) / 4);
   words += (2 * p.TG * p.N + 3) & ~3;
   words += 32;
+  words += p.n_small;
   words += (size_t)p.n_rows * p.RP;
   return words * 4;
 }
@@ -639,7 +714,7 @@ static int fused_launch_t(const FusedProgram& ph, const FusedProgram* prog_dev, 
     smem_set = smem;
   }
   fused_brain_kernel<NMAX><<<grid, kFusedThreads, smem, st>>>(prog_dev, params, node, edge, in_mask, out_mask, y, q_out,
-                                                              partial_dev, head_loss, B, inv_cnt);
+                                                                   partial_dev, head_loss, B, inv_cnt);
   return launch_status("fused_brain_kernel");
 }
 

@@ -27,7 +27,9 @@ struct FusedOp {
   int dxk_tab, dx_tab, n_dx;   // BWD: weight-row index of every requested dx column, its output rows, count (multiple of 4)
   int blk0, nblk;         // BWD: range of global weight-gradient block ids of this layer
   int bias0;              // BWD: first global bias-gradient slot of this layer
-  int pad_[2];            // keep sizeof(FusedOp) a multiple of 16 bytes (shared-memory carve-up alignment)
+  int wt0, nwt;           // BWD: nwt = RS > 0 marks a small layer (blocks split over RS lanes by rows), wt0 = its offset in
+                          // the shared accumulator dWs (sizeof(FusedOp) stays a multiple of 16 bytes)
+                          // (sizeof(FusedOp) stays a multiple of 16 bytes: shared-memory carve-up alignment)
 };
 static_assert(sizeof(FusedOp) % 16 == 0, "FusedOp must stay 16-byte sized");
 
@@ -35,6 +37,7 @@ constexpr int kFusedMaxOps = 48;
 constexpr int kFusedMaxTab = 3072;
 constexpr int kFusedThreads = 384;
 constexpr int kFusedBlkPerThread = 2;
+constexpr int kFusedWarps = kFusedThreads / 32;
 
 struct FusedProgram {
   int n_ops;
@@ -48,6 +51,7 @@ struct FusedProgram {
   int n_blocks;           // weight-gradient 4x4 blocks over all layers
   int n_bias;             // bias-gradient slots over all layers
   int train;              // 1: loss + backward, 0: forward only
+  int n_small;            // floats of the shared weight-gradient accumulator (small layers)
   FusedOp ops[kFusedMaxOps];
   int tab[kFusedMaxTab];
   // block b -> op index, k0, o0 (packed: op<<16 | k0<<8 | o0), bias slot -> op<<16 | o

@@ -170,8 +170,8 @@ int v2v_brain_set_fused(v2v_brain* b, int enable);
 /* Describes the fused program for a batch of B graphs: info8 = {capable, graphs per tile, arena
  * feature rows, shared-memory bytes, phases, weight-gradient blocks, bias slots, table entries}. */
 int v2v_brain_fused_info(v2v_brain* b, int B, int train, int* info8);
-/* Profiling aid: CTA 0 of the fused kernel writes clock64() after every phase of its first tile into
- * dev_buf (>= 49 entries, device memory); NULL disables. */
+/* Profiling aid: lane 0 of every warp of CTA 0 writes clock64() into dev_buf[(phase*12 + warp)*2 + {0: work
+ * done, 1: barrier released}] for its first tile (dev_buf >= 49*12*2 entries, device memory); NULL disables. */
 int v2v_fused_set_trace(long long* dev_buf);
 /* Same query from a configuration alone (host-only, no device needed). */
 int v2v_fused_plan(const v2v_brain_config* cfg, int B, int train, int* info8);

@@ -11,21 +11,26 @@ nd,ed,ad=(torch.from_numpy(t.astype(np.float32)).cuda() for t in (node,edge,adj)
 im,om,_=v2v.pack_adjacency(ad)
 q=brain.forward_device(nd,ed,in_mask=im); y=q+1
 for _ in range(3): brain.train_step_device(nd,ed,im,om,None,y)
-buf=torch.zeros(64,dtype=torch.int64,device='cuda')
+for _ in range(3): brain.train_step_device(nd,ed,im,om,None,y)
+buf=torch.zeros(49*12*2,dtype=torch.int64,device='cuda')
 lib=v2v.load_library()
 assert lib.v2v_fused_set_trace(C.c_void_p(buf.data_ptr()))==0
 brain.train_step_device(nd,ed,im,om,None,y); torch.cuda.synchronize()
 lib.v2v_fused_set_trace(None)
-t=buf.cpu().numpy()
+t=buf.cpu().numpy().reshape(49,12,2)
 nph=brain.fused_info(B,True)['phases']
 names=[]
 for s in range(S): names+= [f'gemm stage{s}',f'agg{s}']
 names+=['mlp1 41x80','mlp2 80x40','mlp3 40x20','mlp4 20x4','loss','bwd mlp4','bwd mlp3','bwd mlp2','bwd mlp1','aggT']
 for s in range(S-1,0,-1): names+=[f'bwd stage{s}','aggT']
 names+=['bwd stage0']
-tot=t[nph]-t[0]
+t0=t[0,:,1].min()
+tot=t[nph,:,1].max()-t0
+print('phase            wall   | per-warp busy cycles (work end - phase start)')
 for i in range(nph):
-    print(f'{names[i] if i<len(names) else i:16s} {t[i+1]-t[i]:8d} cyc  {100*(t[i+1]-t[i])/tot:5.1f}%')
+    start=t[i,:,1].max(); end=t[i+1,:,1].max()
+    busy=(t[i+1,:,0]-t[i,:,1])
+    print(f'{names[i] if i<len(names) else i:14s} {end-start:7d} {100*(end-start)/tot:5.1f}% | '+' '.join(f'{b:6d}' for b in busy))
 print('total',tot,'cycles')
 e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
 e0.record()
