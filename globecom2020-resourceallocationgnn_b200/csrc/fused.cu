@@ -197,15 +197,23 @@ __device__ __forceinline__ void wgrad_block(const FusedOp& op, const float* aren
       xv[i] = *reinterpret_cast<const float4*>(xr[i] + r);
       dv[i] = *reinterpret_cast<const float4*>(dr[i] + r);
     }
+    // 16 independent accumulators per component: dependent FFMAs are 16 instructions apart
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float t = a[i * 4 + j];
-        t = fmaf(xv[i].x, dv[j].x, t); t = fmaf(xv[i].y, dv[j].y, t);
-        t = fmaf(xv[i].z, dv[j].z, t); t = fmaf(xv[i].w, dv[j].w, t);
-        a[i * 4 + j] = t;
-      }
+      for (int j = 0; j < 4; ++j) a[i * 4 + j] = fmaf(xv[i].x, dv[j].x, a[i * 4 + j]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[i * 4 + j] = fmaf(xv[i].y, dv[j].y, a[i * 4 + j]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[i * 4 + j] = fmaf(xv[i].z, dv[j].z, a[i * 4 + j]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a[i * 4 + j] = fmaf(xv[i].w, dv[j].w, a[i * 4 + j]);
   }
 }
 
@@ -285,17 +293,28 @@ __device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* 
         float4 dz[4];
         dz[0] = *reinterpret_cast<const float4*>(ab + zr.x * RP); dz[1] = *reinterpret_cast<const float4*>(ab + zr.y * RP);
         dz[2] = *reinterpret_cast<const float4*>(ab + zr.z * RP); dz[3] = *reinterpret_cast<const float4*>(ab + zr.w * RP);
+        float4 w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = *reinterpret_cast<const float4*>(wr[i] + o);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 w = *reinterpret_cast<const float4*>(wr[i] + o);
-          acc[i].x = fmaf(dz[0].x, w.x, acc[i].x); acc[i].y = fmaf(dz[0].y, w.x, acc[i].y);
-          acc[i].z = fmaf(dz[0].z, w.x, acc[i].z); acc[i].w = fmaf(dz[0].w, w.x, acc[i].w);
-          acc[i].x = fmaf(dz[1].x, w.y, acc[i].x); acc[i].y = fmaf(dz[1].y, w.y, acc[i].y);
-          acc[i].z = fmaf(dz[1].z, w.y, acc[i].z); acc[i].w = fmaf(dz[1].w, w.y, acc[i].w);
-          acc[i].x = fmaf(dz[2].x, w.z, acc[i].x); acc[i].y = fmaf(dz[2].y, w.z, acc[i].y);
-          acc[i].z = fmaf(dz[2].z, w.z, acc[i].z); acc[i].w = fmaf(dz[2].w, w.z, acc[i].w);
-          acc[i].x = fmaf(dz[3].x, w.w, acc[i].x); acc[i].y = fmaf(dz[3].y, w.w, acc[i].y);
-          acc[i].z = fmaf(dz[3].z, w.w, acc[i].z); acc[i].w = fmaf(dz[3].w, w.w, acc[i].w);
+          acc[i].x = fmaf(dz[0].x, w[i].x, acc[i].x); acc[i].y = fmaf(dz[0].y, w[i].x, acc[i].y);
+          acc[i].z = fmaf(dz[0].z, w[i].x, acc[i].z); acc[i].w = fmaf(dz[0].w, w[i].x, acc[i].w);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[i].x = fmaf(dz[1].x, w[i].y, acc[i].x); acc[i].y = fmaf(dz[1].y, w[i].y, acc[i].y);
+          acc[i].z = fmaf(dz[1].z, w[i].y, acc[i].z); acc[i].w = fmaf(dz[1].w, w[i].y, acc[i].w);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[i].x = fmaf(dz[2].x, w[i].z, acc[i].x); acc[i].y = fmaf(dz[2].y, w[i].z, acc[i].y);
+          acc[i].z = fmaf(dz[2].z, w[i].z, acc[i].z); acc[i].w = fmaf(dz[2].w, w[i].z, acc[i].w);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[i].x = fmaf(dz[3].x, w[i].w, acc[i].x); acc[i].y = fmaf(dz[3].y, w[i].w, acc[i].y);
+          acc[i].z = fmaf(dz[3].z, w[i].w, acc[i].z); acc[i].w = fmaf(dz[3].w, w[i].w, acc[i].w);
         }
       }
 #pragma unroll
@@ -585,6 +604,14 @@ int fused_build_program(const FusedShape& s, int TG, int train, FusedProgram* ou
     lo->type = FOP_LOSS;
     b.release(yR);   // dead after the loss phase
     int blk = 0, bias = 0;
+    // the layer with the most 4x4 blocks (<= one per thread) keeps them in registers across tiles; every other
+    // layer row-splits its blocks and accumulates in the CTA's shared buffer
+    int reg_layer = -1, reg_blocks = 0;
+    for (int l = 0; l < s.n_layers; ++l) {
+      const int K_act = (l == 0) ? (Dn + De) : s.layer_K[l];
+      const int nb = ((K_act + 3) / 4) * (s.layer_O[l] / 4);
+      if (nb <= kFusedThreads * kFusedBlkPerThread && nb > reg_blocks) { reg_blocks = nb; reg_layer = l; }
+    }
     auto add_bwd = [&](int l, const std::vector<int>& dz, const std::vector<int>& dxk, const std::vector<int>& dx,
                        const std::vector<int>& gate) -> int {
       FusedOp* o = b.add_op();
@@ -599,7 +626,7 @@ int fused_build_program(const FusedShape& s, int TG, int train, FusedProgram* ou
       o->blk0 = blk;
       const int kb_n = (o->K + 3) / 4, ob_n = o->O / 4;
       o->nblk = kb_n * ob_n;
-      const bool small = o->nblk <= 96;
+      const bool small = (l != reg_layer);
       if (small) {                 // row-split weight gradient into the shared accumulator (wt0 = offset, nwt = RS)
         int rs = 1;
         while (rs < 8 && o->nblk * rs * 2 <= kFusedThreads) rs *= 2;

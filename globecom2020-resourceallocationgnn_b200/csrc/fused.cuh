@@ -36,7 +36,7 @@ static_assert(sizeof(FusedOp) % 16 == 0, "FusedOp must stay 16-byte sized");
 constexpr int kFusedMaxOps = 48;
 constexpr int kFusedMaxTab = 3072;
 constexpr int kFusedThreads = 384;
-constexpr int kFusedBlkPerThread = 2;
+constexpr int kFusedBlkPerThread = 1;
 constexpr int kFusedWarps = kFusedThreads / 32;
 
 struct FusedProgram {
