@@ -111,6 +111,15 @@ __global__ void adj_pack_kernel(const float* __restrict__ adj, int B, int N, int
 // ---------------------------------------------------------------------------
 constexpr int kAggWarps = 8;        // warps per CTA (2 CTAs per SM when shared memory allows)
 
+static int agg_block_min_n() {      // tunable for experiments: V2V_AGG_BLOCK_MIN_N
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("V2V_AGG_BLOCK_MIN_N");
+    v = e ? atoi(e) : 96;          // measured: warp-per-graph wins up to N = 64, CTA-per-graph from N = 128
+  }
+  return v;
+}
+
 template <typename T, int MT, int MP>
 static int launch_fast(const T* H, const uint32_t* mask, const T* addend, T* out, int B, int N, bool independent,
                        cudaStream_t st) {
@@ -127,12 +136,17 @@ static int agg_mask_dispatch(const T* H, const uint32_t* mask, const T* addend, 
                              int F, bool independent, cudaStream_t st) {
   const bool aligned = ((((uintptr_t)H) | ((uintptr_t)out) | ((uintptr_t)mask) | ((uintptr_t)addend)) & 15u) == 0;
   const bool add = addend != nullptr;
-  if (F == 16 && N <= 32 && aligned && B > 0) {
+  if (F == 16 && N <= 20 && aligned && B > 0) {
+    // small graphs: dense predicated gather-reduce (profiles/agg_variants_r01.txt)
     if (N <= 8 && agg_fast_fits<T>(N, 8, add, kAggWarps, 1)) return launch_fast<T, 8, 1>(H, mask, addend, out, B, N, independent, st);
-    // N <= 20: 2-graph tiles (16 lanes per graph, 5 targets per lane) pipeline best (profiles/agg_variants_r01.txt)
-    if (N <= 20 && agg_fast_fits<T>(N, 2, add, kAggWarps, 1)) return launch_fast<T, 5, 4>(H, mask, addend, out, B, N, independent, st);
-    if (agg_fast_fits<T>(N, 4, add, kAggWarps, 1)) return launch_fast<T, 16, 2>(H, mask, addend, out, B, N, independent, st);
-    if (agg_fast_fits<T>(N, 2, add, kAggWarps, 1)) return launch_fast<T, 8, 4>(H, mask, addend, out, B, N, independent, st);
+    if (agg_fast_fits<T>(N, 2, add, kAggWarps, 1)) return launch_fast<T, 5, 4>(H, mask, addend, out, B, N, independent, st);
+  }
+  if (F == 16 && N <= 256 && aligned && B > 0) {
+    // larger graphs: set-bit / clear-bit walk (work ~ N * min(deg, N - deg)); one warp per graph tile up to
+    // kAggBlockMinN nodes, one CTA per graph beyond (addend aliasing out is fine: same thread reads then writes)
+    const int rc = (N >= agg_block_min_n()) ? launch_agg_block<T>(H, mask, addend, out, B, N, !independent, st)
+                                            : launch_agg_sparse<T>(H, mask, addend, out, B, N, !independent, st);
+    if (rc >= 0) return rc;
   }
   const int W = ceil_div(N, 32);
   long total = (long)B * N * F;

@@ -193,6 +193,243 @@ agg_mask_f16_kernel(const T* __restrict__ H, const uint32_t* __restrict__ mask,
 }
 
 // ---------------------------------------------------------------------------
+// Large graphs (20 < N <= 256): same TMA ring, but the N^2 predicated adds of the dense form would make the kernel
+// FP32-bound (26 adds per byte at N = 256).  Per target the kernel walks only the set bits of its mask -- or, when
+// more than half of the bits are set (the reference adjacency has in-degree N-2, BS_brain.py:441-445), the CLEAR
+// bits, subtracting them from the graph's column total.  Work is O(N * min(deg, N - deg)) and the kernel stays
+// HBM-bound for both the reference-dense and the sparse variants.  (fp32 rounding differs from the sequential sum
+// by a few ulp of sum|H|, far inside the 1e-4 parity bar.)
+// ---------------------------------------------------------------------------
+struct AggSparseSizes {
+  int h_bytes, mask_off, stage_bytes, out_bytes, warp_bytes;
+};
+template <typename T>
+__host__ __device__ inline AggSparseSizes agg_sparse_sizes(int N, int W, int TG, bool has_addend) {
+  AggSparseSizes s;
+  s.h_bytes = TG * N * 16 * (int)sizeof(T);
+  s.mask_off = s.h_bytes * (has_addend ? 2 : 1);
+  s.stage_bytes = (s.mask_off + TG * N * W * 4 + 127) & ~127;
+  s.out_bytes = (s.h_bytes + 127) & ~127;
+  s.warp_bytes = kAggStages * s.stage_bytes + s.out_bytes;
+  return s;
+}
+
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+
+template <typename T, bool ADD, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+agg_sparse_f16_kernel(const T* __restrict__ H, const uint32_t* __restrict__ mask, const T* __restrict__ addend,
+                      T* __restrict__ out, int B, int N, int W, int TG, int dep_wait) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[WARPS][kAggStages];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = lane & 3, tl = lane >> 2;                       // feature quad, target lane (8 targets in flight)
+  const AggSparseSizes ts = agg_sparse_sizes<T>(N, W, TG, ADD);
+  uint8_t* wbase = smem_raw + (size_t)warp * ts.warp_bytes;
+  uint8_t* out_s = wbase + kAggStages * ts.stage_bytes;
+  const int g_begin = (int)(((long)B * blockIdx.x) / gridDim.x);
+  const int g_end = (int)(((long)B * (blockIdx.x + 1)) / gridDim.x);
+  const int num_tiles = (g_end - g_begin + TG - 1) / TG;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kAggStages; ++s) mbar_init(&bars[warp][s], 1);
+    fence_async_smem();
+  }
+  __syncwarp();
+  pdl_launch_dependents();
+  if (dep_wait) pdl_wait();
+  const size_t graph_elems = (size_t)N * 16;
+  auto issue = [&](int t, int s) {     // lane 0 only
+    const int g0 = g_begin + t * TG;
+    const int ng = min(TG, g_end - g0);
+    const uint32_t hb = (uint32_t)(ng * N * 16 * sizeof(T));
+    const uint32_t mb = (uint32_t)(ng * N * W * 4);
+    const bool mask_bulk = ((((uint32_t)g0 * (uint32_t)(N * W) * 4u) | mb) & 15u) == 0;
+    uint8_t* st = wbase + s * ts.stage_bytes;
+    mbar_arrive_expect_tx(&bars[warp][s], hb + (ADD ? hb : 0) + (mask_bulk ? mb : 0));
+    bulk_g2s(st, H + (size_t)g0 * graph_elems, hb, &bars[warp][s]);
+    if (ADD) bulk_g2s(st + ts.h_bytes, addend + (size_t)g0 * graph_elems, hb, &bars[warp][s]);
+    if (mask_bulk) bulk_g2s(st + ts.mask_off, mask + (size_t)g0 * N * W, mb, &bars[warp][s]);
+  };
+  int tile = warp;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kAggStages; ++s) {
+      const int t = tile + s * WARPS;
+      if (t < num_tiles) issue(t, s);
+    }
+  }
+  const uint32_t last_valid = (N & 31) ? ((1u << (N & 31)) - 1u) : 0xffffffffu;
+  uint32_t phase = 0;
+  int stage = 0;
+  for (; tile < num_tiles; tile += WARPS) {
+    const int g0 = g_begin + tile * TG;
+    const int ng = min(TG, g_end - g0);
+    uint8_t* st = wbase + stage * ts.stage_bytes;
+    const T* Hs = reinterpret_cast<const T*>(st);
+    const T* As = reinterpret_cast<const T*>(st + ts.h_bytes);
+    uint32_t* Ms = reinterpret_cast<uint32_t*>(st + ts.mask_off);
+    if (((((uint32_t)g0 * (uint32_t)(N * W) * 4u) | (uint32_t)(ng * N * W * 4)) & 15u) != 0) {
+      for (int i = lane; i < ng * N * W; i += 32) Ms[i] = mask[(size_t)g0 * N * W + i];
+      __syncwarp();
+    }
+    mbar_wait(&bars[warp][stage], (phase >> stage) & 1u);
+    if (lane == 0) bulk_wait_read<0>();            // the previous tile's store has drained out_s
+    __syncwarp();
+    T* Os = reinterpret_cast<T*>(out_s);
+    for (int g = 0; g < ng; ++g) {
+      const T* Hg = Hs + (size_t)g * graph_elems + c * 4;
+      const uint32_t* Mg = Ms + (size_t)g * N * W;
+      float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int n = tl; n < N; n += 8) tot = f4_add(tot, ld_row4(Hg + n * 16));
+#pragma unroll
+      for (int off = 4; off < 32; off <<= 1) {
+        tot.x += __shfl_xor_sync(0xffffffffu, tot.x, off); tot.y += __shfl_xor_sync(0xffffffffu, tot.y, off);
+        tot.z += __shfl_xor_sync(0xffffffffu, tot.z, off); tot.w += __shfl_xor_sync(0xffffffffu, tot.w, off);
+      }
+      for (int m = tl; m < N; m += 8) {
+        const uint32_t* mm = Mg + m * W;
+        int cnt = 0;
+        for (int w = 0; w < W; ++w) cnt += __popc(mm[w]);
+        const bool dense = 2 * cnt > N;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int w = 0; w < W; ++w) {
+          uint32_t bits = mm[w];
+          if (dense) bits = ~bits & (w == W - 1 ? last_valid : 0xffffffffu);
+          while (bits) {
+            const int n = w * 32 + __ffs(bits) - 1;
+            bits &= bits - 1;
+            acc = f4_add(acc, ld_row4(Hg + n * 16));
+          }
+        }
+        float4 r = dense ? f4_sub(tot, acc) : acc;
+        if (ADD) r = f4_add(r, ld_row4(As + ((size_t)(g * N + m) * 16 + c * 4)));
+        st_row4(Os + ((size_t)(g * N + m) * 16 + c * 4), r);
+      }
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      bulk_s2g(out + (size_t)g0 * graph_elems, out_s, (uint32_t)(ng * N * 16 * sizeof(T)));
+      bulk_commit();
+      const int nt = tile + kAggStages * WARPS;
+      if (nt < num_tiles) issue(nt, stage);          // the stage itself was only read: refill immediately
+    }
+    phase ^= (1u << stage);
+    stage = (stage + 1 == kAggStages) ? 0 : stage + 1;
+  }
+  if (lane == 0) bulk_wait_read<0>();
+}
+
+// ---------------------------------------------------------------------------
+// Very large graphs (N > 64): one CTA per graph.  The graph's H rows and mask words arrive by bulk-async
+// copy; 256 threads = 64 targets x 4 feature quads walk the set / clear bits as above, several CTAs are
+// resident per SM so one graph's load overlaps another's walk; results go straight to global memory
+// (a warp writes 8 consecutive 64-byte rows).
+// ---------------------------------------------------------------------------
+template <typename T, bool ADD>
+__global__ void __launch_bounds__(256)
+agg_block_f16_kernel(const T* __restrict__ H, const uint32_t* __restrict__ mask, const T* __restrict__ addend,
+                     T* __restrict__ out, int B, int N, int W, int dep_wait) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ float4 tot_s[8][4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = tid & 3, part = tid >> 2;                         // 64 targets in flight
+  const size_t graph_elems = (size_t)N * 16;
+  const uint32_t hb = (uint32_t)(graph_elems * sizeof(T));
+  const uint32_t mb = (uint32_t)(N * W * 4);
+  T* Hs = reinterpret_cast<T*>(smem_raw);
+  uint32_t* Ms = reinterpret_cast<uint32_t*>(smem_raw + hb);
+  if (tid == 0) { mbar_init(&bar, 1); fence_async_smem(); }
+  __syncthreads();
+  pdl_launch_dependents();
+  if (dep_wait) pdl_wait();
+  const uint32_t last_valid = (N & 31) ? ((1u << (N & 31)) - 1u) : 0xffffffffu;
+  uint32_t phase = 0;
+  for (int g = blockIdx.x; g < B; g += gridDim.x) {
+    const bool mask_bulk = (((uint32_t)((size_t)g * N * W * 4) | mb) & 15u) == 0;
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&bar, hb + (mask_bulk ? mb : 0));
+      bulk_g2s(Hs, H + (size_t)g * graph_elems, hb, &bar);
+      if (mask_bulk) bulk_g2s(Ms, mask + (size_t)g * N * W, mb, &bar);
+    }
+    if (!mask_bulk) for (int i = tid; i < N * W; i += 256) Ms[i] = mask[(size_t)g * N * W + i];
+    __syncthreads();
+    mbar_wait(&bar, phase);
+    phase ^= 1u;
+    const T* Hg = Hs + c * 4;
+    float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int n = part; n < N; n += 64) tot = f4_add(tot, ld_row4(Hg + n * 16));
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) {
+      tot.x += __shfl_xor_sync(0xffffffffu, tot.x, off); tot.y += __shfl_xor_sync(0xffffffffu, tot.y, off);
+      tot.z += __shfl_xor_sync(0xffffffffu, tot.z, off); tot.w += __shfl_xor_sync(0xffffffffu, tot.w, off);
+    }
+    if (lane < 4) tot_s[warp][lane] = tot;
+    __syncthreads();
+    tot = tot_s[0][c];
+#pragma unroll
+    for (int w8 = 1; w8 < 8; ++w8) tot = f4_add(tot, tot_s[w8][c]);
+    for (int m = part; m < N; m += 64) {
+      const uint32_t* mm = Ms + m * W;
+      int cnt = 0;
+      for (int w = 0; w < W; ++w) cnt += __popc(mm[w]);
+      const bool dense = 2 * cnt > N;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int w = 0; w < W; ++w) {
+        uint32_t bits = mm[w];
+        if (dense) bits = ~bits & (w == W - 1 ? last_valid : 0xffffffffu);
+        while (bits) {
+          const int n = w * 32 + __ffs(bits) - 1;
+          bits &= bits - 1;
+          acc = f4_add(acc, ld_row4(Hg + n * 16));
+        }
+      }
+      float4 r = dense ? f4_sub(tot, acc) : acc;
+      const size_t o = (size_t)g * graph_elems + (size_t)m * 16 + c * 4;
+      if (ADD) r = f4_add(r, ld_row4(addend + o));
+      st_row4(out + o, r);
+    }
+    __syncthreads();                     // everyone is done with Hs / Ms / tot_s before the next graph lands
+  }
+}
+
+template <typename T>
+static int launch_agg_block(const T* H, const uint32_t* mask, const T* addend, T* out, int B, int N, bool dep_wait,
+                            cudaStream_t st) {
+  const int W = ceil_div(N, 32);
+  const size_t smem = (size_t)N * 16 * sizeof(T) + (size_t)N * W * 4 + 128;
+  if (smem > 200 * 1024) return -1;
+  const int per_sm = std::max(1, std::min(8, (int)((220 * 1024) / (smem + 1024))));
+  const int grid = std::max(1, std::min(B, sm_count() * per_sm));
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3(grid);
+  lc.blockDim = dim3(256);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = 1;
+  const int dep = dep_wait ? 1 : 0;
+  if (addend) {
+    auto k = agg_block_f16_kernel<T, true>;
+    static size_t smem_set = 0;
+    if (smem > smem_set) { V2V_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
+    V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, k, H, mask, addend, out, B, N, W, dep));
+  } else {
+    auto k = agg_block_f16_kernel<T, false>;
+    static size_t smem_set = 0;
+    if (smem > smem_set) { V2V_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
+    V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, k, H, mask, addend, out, B, N, W, dep));
+  }
+  return launch_status("agg_block_f16_kernel");
+}
+
+// ---------------------------------------------------------------------------
 // launch helper (programmatic dependent launch)
 // ---------------------------------------------------------------------------
 struct AggLaunchCfg {
@@ -228,6 +465,57 @@ static int launch_agg_fast(const T* H, const uint32_t* mask, const T* addend, T*
   const int dep = cfg.dep_wait ? 1 : 0;
   V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, k, H, mask, addend, out, B, N, dep));
   return launch_status("agg_mask_f16_kernel");
+}
+
+template <typename T, bool ADD, int WARPS>
+static int launch_agg_sparse_t(const T* H, const uint32_t* mask, const T* addend, T* out, int B, int N, int W, int TG,
+                               bool dep_wait, cudaStream_t st) {
+  AggSparseSizes ts = agg_sparse_sizes<T>(N, W, TG, ADD);
+  const size_t smem = (size_t)ts.warp_bytes * WARPS;
+  const int num_tiles = ceil_div(B, TG);
+  const int ctas_per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
+  const int grid = std::max(1, std::min(ceil_div(num_tiles, WARPS), sm_count() * std::min(ctas_per_sm, 4)));
+  auto k = agg_sparse_f16_kernel<T, ADD, WARPS>;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    V2V_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3(grid);
+  lc.blockDim = dim3(WARPS * 32);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = 1;
+  const int dep = dep_wait ? 1 : 0;
+  V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, k, H, mask, addend, out, B, N, W, TG, dep));
+  return launch_status("agg_sparse_f16_kernel");
+}
+
+// picks the graphs per warp tile (~4 KB of H) and the warps per CTA that fit shared memory
+template <typename T>
+static int launch_agg_sparse(const T* H, const uint32_t* mask, const T* addend, T* out, int B, int N, bool dep_wait,
+                             cudaStream_t st) {
+  const int W = ceil_div(N, 32);
+  const bool add = addend != nullptr;
+  int TG = std::max(1, 4096 / (N * 16 * (int)sizeof(T)));
+  while (TG > 1 && ((TG * N * W * 4) & 15)) --TG;               // keep the mask span 16-byte sized for the bulk copy
+  AggSparseSizes ts = agg_sparse_sizes<T>(N, W, TG, add);
+  const size_t budget = 224 * 1024;
+  if ((size_t)ts.warp_bytes * 8 <= budget)
+    return add ? launch_agg_sparse_t<T, true, 8>(H, mask, addend, out, B, N, W, TG, dep_wait, st)
+               : launch_agg_sparse_t<T, false, 8>(H, mask, addend, out, B, N, W, TG, dep_wait, st);
+  if ((size_t)ts.warp_bytes * 4 <= budget)
+    return add ? launch_agg_sparse_t<T, true, 4>(H, mask, addend, out, B, N, W, TG, dep_wait, st)
+               : launch_agg_sparse_t<T, false, 4>(H, mask, addend, out, B, N, W, TG, dep_wait, st);
+  if ((size_t)ts.warp_bytes * 2 <= budget)
+    return add ? launch_agg_sparse_t<T, true, 2>(H, mask, addend, out, B, N, W, TG, dep_wait, st)
+               : launch_agg_sparse_t<T, false, 2>(H, mask, addend, out, B, N, W, TG, dep_wait, st);
+  return -1;   // does not fit: caller falls back to the generic kernel
 }
 
 template <typename T>
