@@ -315,7 +315,11 @@ def run_engine_arm(a):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "global_batch": world * B, "graphs_per_gpu": B, "nodes": N, "stages": S,
                        "parallelism": f"dp{world}" if world > 1 else "single",
-                       "collective": "one NCCL sum all-reduce of the flat fp32 gradient per step" if world > 1 else "none",
+                       "collective": ("none" if world == 1 else
+                                      ("one fused kernel per step: per-CTA partial reduction + gradient push to all peers over "
+                                       "NVLink (cudaIpc peer stores, per-chunk epoch flags) + rank-ordered sum + Keras-Adam"
+                                       if brain._comm is not None else
+                                       "one NCCL sum all-reduce of the flat fp32 gradient per step, then the Adam kernel")),
                        "l2": f"rotating pool of {R} distinct device-resident input batches ({R * per_batch / 2**20:.0f} MiB "
                              f"> 126 MiB L2); roofline loop rotates over buffer sets > L2 as well",
                        "final_loss": loss_now},

@@ -71,6 +71,17 @@ SIGNATURES = {
     "v2v_brain_forward_backward": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                              C.c_int, c_void_p, c_void_p]),
     "v2v_brain_apply_adam": (C.c_int, [c_void_p, C.c_float, c_void_p]),
+    "v2v_comm_create": (C.c_int, [C.c_long, C.c_int, C.c_int, C.POINTER(c_void_p)]),
+    "v2v_comm_destroy": (None, [c_void_p]),
+    "v2v_comm_ipc_handle_bytes": (C.c_int, []),
+    "v2v_comm_get_ipc_handle": (C.c_int, [c_void_p, c_void_p]),
+    "v2v_comm_open_peers": (C.c_int, [c_void_p, c_void_p]),
+    "v2v_comm_allreduce_adam": (C.c_int, [c_void_p, c_void_p, C.c_int, C.c_long, c_void_p, C.c_int, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                          c_void_p]),
+    "v2v_comm_check": (C.c_int, [c_void_p, c_void_p]),
+    "v2v_brain_train_step_dp": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, C.c_int, c_void_p, c_void_p]),
     "v2v_brain_train_step": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        C.c_int, c_void_p, c_void_p]),
     "v2v_brain_predict_host": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, c_void_p,

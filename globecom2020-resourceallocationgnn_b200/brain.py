@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-import re
+import os
 
 import numpy as np
 import torch
@@ -121,8 +121,11 @@ class BS:
             data_parallel = torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1
         self.data_parallel = bool(data_parallel)
+        self._comm = None
         self._create(max(int(max_batch), 1))
         self._init_weights(seed)
+        if self.data_parallel and os.environ.get("V2V_DP_BACKEND", "peer") == "peer":
+            self.enable_peer_allreduce()
         self.model = self._create_model(0)
         self.target_model = self._create_model(1)
 
@@ -157,8 +160,30 @@ class BS:
         self._pin = {}
         self._create(int(2 ** math.ceil(math.log2(B))), keep_state=state)
 
+    def enable_peer_allreduce(self, group=None):
+        """Replace the NCCL gradient all-reduce + Adam kernel by ONE kernel that exchanges the gradient over
+        NVLink peer memory (cudaIpc-mapped buffers) and applies Adam (csrc/comm.cu).  Collective: every rank
+        of the group must call it.  The handles travel through torch.distributed (plumbing)."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        comm = C.c_void_p()
+        _lib.check(self._lib.v2v_comm_create(self.param_count + 32, world, rank, C.byref(comm)))
+        nb = self._lib.v2v_comm_ipc_handle_bytes()
+        mine = C.create_string_buffer(nb)
+        _lib.check(self._lib.v2v_comm_get_ipc_handle(comm, mine))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, bytes(mine.raw), group=group)
+        blob = C.create_string_buffer(b"".join(gathered), nb * world)
+        _lib.check(self._lib.v2v_comm_open_peers(comm, blob))
+        dist.barrier(group)
+        self._comm = comm
+
     def __del__(self):
         try:
+            if getattr(self, "_comm", None) is not None:
+                torch.cuda.synchronize()
+                self._lib.v2v_comm_destroy(self._comm)
+                self._comm = None
             if self._handle is not None:
                 self._lib.v2v_brain_destroy(self._handle)
                 self._handle = None
@@ -464,6 +489,11 @@ class BS:
         if not self.data_parallel:
             _lib.check(self._lib.v2v_brain_train_step(self._handle, ptr(node), ptr(edge), ptr(neighbor), ptr(in_mask),
                                                       ptr(out_mask), ptr(adj), ptr(y), B, ptr(head_loss), st), ValueError)
+            return head_loss
+        if self._comm is not None:              # fused reduce + NVLink exchange + Adam (one kernel)
+            _lib.check(self._lib.v2v_brain_train_step_dp(self._handle, self._comm, ptr(node), ptr(edge), ptr(neighbor),
+                                                         ptr(in_mask), ptr(out_mask), ptr(adj), ptr(y), B, ptr(head_loss),
+                                                         st), ValueError)
             return head_loss
         import torch.distributed as dist
         _lib.check(self._lib.v2v_brain_forward_backward(self._handle, ptr(node), ptr(edge), ptr(neighbor), ptr(in_mask),

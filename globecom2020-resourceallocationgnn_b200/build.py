@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_NAME = "libv2vgnn_b200.so"
 LIB_PATH = os.path.join(HERE, LIB_NAME)
-SOURCES = ["agg.cu", "dense.cu", "loss_opt.cu", "fused.cu", "brain.cu"]
+SOURCES = ["agg.cu", "dense.cu", "loss_opt.cu", "fused.cu", "comm.cu", "brain.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -482,6 +482,29 @@ extern "C" int v2v_brain_train_step(v2v_brain* b, const float* node, const float
   return v2v_brain_apply_adam(b, 1.f, stream);
 }
 
+// Data-parallel train step: local fwd + Huber + bwd, then ONE kernel that reduces the per-CTA partials,
+// exchanges the gradient (and the per-head losses) with all peers over NVLink and applies Adam (comm.cu).
+extern "C" int v2v_comm_allreduce_adam(struct v2v_comm* c, const float* partial_dev, int n_cta, long n_src,
+                                       const float* extra_dev, int n_extra, float* grad_dev, float* p_dev,
+                                       float* m_dev, float* v_dev, float* extra_out_dev, int t, float lr, float beta1,
+                                       float beta2, float eps, void* stream);
+
+extern "C" int v2v_brain_train_step_dp(v2v_brain* b, struct v2v_comm* comm, const float* node, const float* edge,
+                                       const float* neigh, const uint32_t* in_mask, const uint32_t* out_mask,
+                                       const float* adj, const float* y, int B, float* head_loss_dev, void* stream) {
+  V2V_REQUIRE(b && comm, "v2v_brain_train_step_dp: null argument");
+  float* hl = head_loss_dev ? head_loss_dev : b->head_loss;
+  b->defer_reduce = true;
+  int rc = v2v_brain_forward_backward(b, node, edge, neigh, in_mask, out_mask, adj, y, B, hl, stream);
+  b->defer_reduce = false;
+  if (rc) return rc;
+  b->iterations += 1;
+  const bool fused = b->last_grid > 0;
+  return v2v_comm_allreduce_adam(comm, fused ? b->partial : b->params[2], fused ? b->last_grid : 1, (long)b->n_params, hl,
+                                 b->N, b->params[2], b->params[0], b->params[3], b->params[4], hl, b->iterations, b->cfg.lr,
+                                 b->cfg.beta1, b->cfg.beta2, b->cfg.eps, stream);
+}
+
 // ---------------------------------------------------------------------------
 // host-buffer entry points (the reference-facing plugin path)
 // ---------------------------------------------------------------------------

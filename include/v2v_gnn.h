@@ -203,6 +203,31 @@ int v2v_brain_forward_backward(v2v_brain* b, const float* node_dev, const float*
 /* iterations += 1; Keras-Adam on the online parameters with g * grad_scale */
 int v2v_brain_apply_adam(v2v_brain* b, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Data parallelism (one process per GPU).  The reference has no distributed path; every batch row is an
+ * independent graph, so ranks own contiguous batch shards and exchange ONE flat gradient per step.
+ * v2v_comm is that exchange over NVLink peer memory (cudaIpc): create one per rank with the payload size
+ * (parameters + num_d2d per-head losses), all-gather the handles by any means (torch.distributed here), open.
+ * v2v_comm_allreduce_adam = reduce the local per-CTA partials + push to every peer + wait + sum in rank order +
+ * Keras-Adam (BS_brain.py:212), in ONE kernel.  All ranks must call it the same number of times.
+ * ---------------------------------------------------------------------- */
+typedef struct v2v_comm v2v_comm;
+int v2v_comm_create(long n_floats, int world, int rank, v2v_comm** out);
+void v2v_comm_destroy(v2v_comm* c);
+int v2v_comm_ipc_handle_bytes(void);
+int v2v_comm_get_ipc_handle(v2v_comm* c, void* handle_out);
+int v2v_comm_open_peers(v2v_comm* c, const void* handles /* world blobs in rank order */);
+int v2v_comm_allreduce_adam(v2v_comm* c, const float* partial_dev, int n_cta, long n_src,
+                            const float* extra_dev, int n_extra, float* grad_dev, float* p_dev,
+                            float* m_dev, float* v_dev, float* extra_out_dev, int t, float lr, float beta1,
+                            float beta2, float eps, void* stream);
+int v2v_comm_check(v2v_comm* c, void* stream);
+/* data-parallel train_dnn: local fwd + Huber + bwd, then v2v_comm_allreduce_adam; head_loss_dev receives the
+ * per-head losses averaged over ranks */
+int v2v_brain_train_step_dp(v2v_brain* b, v2v_comm* comm, const float* node_dev, const float* edge_dev,
+                            const float* neighbor_dev, const uint32_t* in_mask_dev, const uint32_t* out_mask_dev,
+                            const float* adj_dev, const float* y_dev, int B, float* head_loss_dev, void* stream);
+
 /* train_dnn (BS_brain.py:218-223) == one fwd+bwd+Adam step on exactly B rows. */
 int v2v_brain_train_step(v2v_brain* b, const float* node_dev, const float* edge_dev,
                          const float* neighbor_dev,

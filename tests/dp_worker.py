@@ -1,0 +1,74 @@
+"""Run under torchrun with >= 2 GPUs: the data-parallel train step with (a) the fused NVLink peer exchange + Adam kernel
+and (b) NCCL all-reduce + Adam must both reproduce the single-process full-batch step (tests/test_gpu_dp.py)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import v2v_gnn_b200 as v2v                      # noqa: E402
+from oracle import v2v_oracle as O               # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    N, S, Bl = 20, 2, 96
+    rng = np.random.default_rng(5)
+    node, edge, adj, _ = O.synth_batch(Bl * world, N, rng)
+    node, edge, adj = node.astype(np.float32), edge.astype(np.float32), adj.astype(np.float32)
+    y = rng.normal(0, 1, (Bl * world, N, 4)).astype(np.float32)
+    d = O.BrainDims(N, stages=S, per_slot=False)
+    p0 = O.flatten_params(O.init_params(d, np.random.default_rng(9), bias_scale=0.05)).astype(np.float32)
+    lo, hi = rank * Bl, (rank + 1) * Bl
+    dev = lambda a: torch.from_numpy(a).cuda()
+    results = {}
+    for backend in ("peer", "nccl"):
+        os.environ["V2V_DP_BACKEND"] = backend
+        brain = v2v.BS(N, 3, 1, 16, 1, 4, stages=S, per_slot=False, max_batch=Bl * world, data_parallel=True, seed=1)
+        assert (brain._comm is not None) == (backend == "peer")
+        brain.set_flat_params(p0, 0)
+        im, om, _ = v2v.pack_adjacency(dev(adj[lo:hi]))
+        losses = []
+        for _ in range(3):
+            hl = brain.train_step_device(dev(node[lo:hi]), dev(edge[lo:hi]), im, om, None, dev(y[lo:hi]))
+            losses.append(hl.clone())
+        if brain._comm is not None:
+            v2v._lib.check(brain._lib.v2v_comm_check(brain._comm, v2v._lib.current_stream()))
+        torch.cuda.synchronize()
+        results[backend] = (brain.get_flat_params(0), brain.get_flat_params(2), torch.stack(losses).cpu().numpy())
+        # every rank must hold bit-identical parameters
+        mine = torch.from_numpy(results[backend][0]).cuda()
+        ref = mine.clone()
+        dist.broadcast(ref, src=0)
+        assert torch.equal(mine, ref), f"{backend}: replicas diverged"
+        del brain
+    # single-process full-batch reference on rank 0's GPU (every rank computes it: cheap)
+    os.environ["V2V_DP_BACKEND"] = "nccl"
+    single = v2v.BS(N, 3, 1, 16, 1, 4, stages=S, per_slot=False, max_batch=Bl * world, data_parallel=False, seed=1)
+    single.set_flat_params(p0, 0)
+    im, om, _ = v2v.pack_adjacency(dev(adj))
+    sl = []
+    for _ in range(3):
+        sl.append(single.train_step_device(dev(node), dev(edge), im, om, None, dev(y)).clone())
+    ps, gs = single.get_flat_params(0), single.get_flat_params(2)
+    sl = torch.stack(sl).cpu().numpy()
+    for backend in ("peer", "nccl"):
+        p, g, l = results[backend]
+        gerr = np.abs(g - gs).max() / np.abs(gs).max()
+        assert gerr < 5e-5, (backend, gerr)
+        assert np.abs(p - ps).max() < 2e-4 and np.quantile(np.abs(p - ps), 0.9) < 2e-6, backend
+    # the peer path carries the per-head losses through the same exchange: global mean on every rank
+    assert np.abs(results["peer"][2] - sl).max() < 1e-4 * np.abs(sl).max()
+    dist.barrier()
+    if rank == 0:
+        print("DP_WORKER_OK world", world)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
