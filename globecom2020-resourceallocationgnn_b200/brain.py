@@ -498,7 +498,7 @@ class BS:
         import torch.distributed as dist
         _lib.check(self._lib.v2v_brain_forward_backward(self._handle, ptr(node), ptr(edge), ptr(neighbor), ptr(in_mask),
                                                         ptr(out_mask), ptr(adj), ptr(y), B, ptr(head_loss), st), ValueError)
-        world = dist.get_world_size()
-        dist.all_reduce(self._views[2], op=dist.ReduceOp.SUM)            # the one collective of the step
-        _lib.check(self._lib.v2v_brain_apply_adam(self._handle, 1.0 / world, st))
+        # the one collective of the step; AVG leaves the global-batch mean gradient in the grad buffer (as the peer path does)
+        dist.all_reduce(self._views[2], op=dist.ReduceOp.AVG)
+        _lib.check(self._lib.v2v_brain_apply_adam(self._handle, 1.0, st))
         return head_loss

@@ -120,15 +120,15 @@ static int agg_block_min_n() {      // tunable for experiments: V2V_AGG_BLOCK_MI
   return v;
 }
 
-template <typename T, int MT, int MP>
+template <typename T, int MT, int MP, int NC = 0>
 static int launch_fast(const T* H, const uint32_t* mask, const T* addend, T* out, int B, int N, bool independent,
                        cudaStream_t st) {
   constexpr int TG = 32 / (4 * MP);
   AggLaunchCfg cfg;
   cfg.dep_wait = !independent;
   cfg.ctas_per_sm = agg_fast_fits<T>(N, TG, addend != nullptr, kAggWarps, 2) ? 2 : 1;
-  if (addend) return launch_agg_fast<T, MT, MP, true, kAggWarps>(H, mask, addend, out, B, N, cfg, st);
-  return launch_agg_fast<T, MT, MP, false, kAggWarps>(H, mask, addend, out, B, N, cfg, st);
+  if (addend) return launch_agg_fast<T, MT, MP, true, kAggWarps, true, NC>(H, mask, addend, out, B, N, cfg, st);
+  return launch_agg_fast<T, MT, MP, false, kAggWarps, true, NC>(H, mask, addend, out, B, N, cfg, st);
 }
 
 template <typename T>
@@ -139,6 +139,8 @@ static int agg_mask_dispatch(const T* H, const uint32_t* mask, const T* addend, 
   if (F == 16 && N <= 20 && aligned && B > 0) {
     // small graphs: dense predicated gather-reduce (profiles/agg_variants_r01.txt)
     if (N <= 8 && agg_fast_fits<T>(N, 8, add, kAggWarps, 1)) return launch_fast<T, 8, 1>(H, mask, addend, out, B, N, independent, st);
+    if (N == 20 && agg_fast_fits<T>(N, 2, add, kAggWarps, 1))       // the north-star shape: compile-time N
+      return launch_fast<T, 5, 4, 20>(H, mask, addend, out, B, N, independent, st);
     if (agg_fast_fits<T>(N, 2, add, kAggWarps, 1)) return launch_fast<T, 5, 4>(H, mask, addend, out, B, N, independent, st);
   }
   if (F == 16 && N <= 256 && aligned && B > 0) {

@@ -72,10 +72,12 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 // T: storage type. MT: targets per lane. MP: target partitions (lanes per graph = 4*MP).
 // WARPS: warps per CTA.  COMPUTE=false turns the kernel into its own data-movement floor (bench only).
-template <typename T, int MT, int MP, bool ADD, int WARPS, bool COMPUTE = true>
+// NC > 0: N is the compile-time constant NC (source walk fully unrolled: row offsets and mask bits become immediates).
+template <typename T, int MT, int MP, bool ADD, int WARPS, bool COMPUTE = true, int NC = 0>
 __global__ void __launch_bounds__(WARPS * 32)
 agg_mask_f16_kernel(const T* __restrict__ H, const uint32_t* __restrict__ mask,
-                    const T* __restrict__ addend, T* __restrict__ out, int B, int N, int dep_wait) {
+                    const T* __restrict__ addend, T* __restrict__ out, int B, int N_rt, int dep_wait) {
+  const int N = NC ? NC : N_rt;
   constexpr int TG = 32 / (4 * MP);           // graphs per warp tile
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[WARPS][kAggStages];
@@ -157,13 +159,24 @@ agg_mask_f16_kernel(const T* __restrict__ H, const uint32_t* __restrict__ mask,
       }
       const T* hrow = Hs + (size_t)gl * N * 16 + c * 4;
       if (gl < ng) {
-#pragma unroll 2
-        for (int n = 0; n < N; ++n) {
-          const float4 v = ld_row4(hrow + n * 16);
-          const uint32_t bit = 1u << n;
+        if (NC) {
 #pragma unroll
-          for (int j = 0; j < MT; ++j) {
-            if (msk[j] & bit) add4(acc[j], v);
+          for (int n = 0; n < NC; ++n) {
+            const float4 v = ld_row4(hrow + n * 16);
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+              if (msk[j] & (1u << n)) add4(acc[j], v);
+            }
+          }
+        } else {
+#pragma unroll 2
+          for (int n = 0; n < N; ++n) {
+            const float4 v = ld_row4(hrow + n * 16);
+            const uint32_t bit = 1u << n;
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+              if (msk[j] & bit) add4(acc[j], v);
+            }
           }
         }
       }
@@ -438,7 +451,7 @@ struct AggLaunchCfg {
   bool dep_wait = true;
 };
 
-template <typename T, int MT, int MP, bool ADD, int WARPS, bool COMPUTE = true>
+template <typename T, int MT, int MP, bool ADD, int WARPS, bool COMPUTE = true, int NC = 0>
 static int launch_agg_fast(const T* H, const uint32_t* mask, const T* addend, T* out, int B, int N,
                            const AggLaunchCfg& cfg, cudaStream_t st) {
   constexpr int TG = 32 / (4 * MP);
@@ -446,7 +459,7 @@ static int launch_agg_fast(const T* H, const uint32_t* mask, const T* addend, T*
   const size_t smem = (size_t)ts.warp_bytes * WARPS;
   const int num_tiles = ceil_div(B, TG);
   const int grid = std::max(1, std::min(ceil_div(num_tiles, WARPS), sm_count() * cfg.ctas_per_sm));
-  auto k = agg_mask_f16_kernel<T, MT, MP, ADD, WARPS, COMPUTE>;
+  auto k = agg_mask_f16_kernel<T, MT, MP, ADD, WARPS, COMPUTE, NC>;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     V2V_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -2,78 +2,106 @@
 //
 // The data-parallel brain exchanges ONE flat fp32 gradient per step (8,720 floats = 35 KB with shared weights):
 // purely latency-bound, so instead of a library collective followed by an optimiser kernel, ONE kernel
-//   1. reduces this rank's per-CTA gradient partials (fused_brain_kernel output) chunk by chunk,
-//   2. pushes each reduced chunk straight into a slot of every peer's communication buffer (plain stores to
-//      cudaIpc-mapped peer pointers: they travel over NVLink 5 / NVSwitch), fences system-wide and raises a
-//      per-(rank, chunk) epoch flag on every peer,
-//   3. waits for the same chunk of all ranks to land locally, sums the slots in rank order (bit-identical
-//      result on every rank), scales by 1/world and applies the Keras-Adam update (BS_brain.py:212) in place.
-// Chunks are independent: CTA c only ever waits for chunk c, so the transfer of one chunk overlaps the math of
-// another and there is no grid-wide barrier.  Slots are double-buffered by epoch parity: a rank can run at most
-// one epoch ahead of its slowest peer because it needs that peer's flag to finish its own epoch.
+//   1. reduces this rank's per-CTA gradient partials (fused_brain_kernel output), 64 columns per CTA, the partials
+//      split over 8 slices so that every load is independent,
+//   2. pushes each reduced element straight into its slot of every peer's communication buffer as ONE 8-byte store
+//      {value, epoch} to a cudaIpc-mapped peer pointer (NVLink 5 / NVSwitch).  The epoch travels inside the same
+//      atomic 8-byte transaction as the value, so no fence, no separate flag and no second NVLink round trip is
+//      needed (the "low-latency" protocol of collective libraries),
+//   3. polls its own slots until every rank's element carries the current epoch, sums them in rank order
+//      (bit-identical result on every rank), scales by 1/world and applies the Keras-Adam update
+//      (BS_brain.py:212) in place.
+// Elements are independent: a CTA only waits for its own 64 columns, so the transfer of one chunk overlaps the
+// math of another and there is no grid-wide barrier.  Slots are double-buffered by epoch parity: a rank can run
+// at most one epoch ahead of its slowest peer because it needs that peer's values to finish its own epoch.
 #include "v2v_common.cuh"
 
 namespace v2v {
 
-constexpr int kCommChunk = 256;          // floats per CTA
+constexpr int kCommChunk = 64;           // floats per CTA
+constexpr int kCommSlices = 8;           // warps-pairs splitting the sum over the per-CTA partials
+constexpr int kCommThreads = kCommChunk * kCommSlices;
 constexpr int kCommMaxWorld = 16;
 
 struct CommPeers {
-  float* slots[kCommMaxWorld];           // peer r's communication buffer: slots[2][world][n_pad]
-  uint32_t* flags[kCommMaxWorld];        // peer r's flags[world][n_chunks]
+  uint2* slots[kCommMaxWorld];           // peer r's communication buffer: slots[2][world][n_pad] of {value bits, epoch}
 };
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
 }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+// one 8-byte transaction: the epoch can never be observed without its value
+__device__ __forceinline__ void st_ll(uint2* p, float val, uint32_t epoch) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(val)), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ uint2 ld_ll(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
   return v;
 }
 
-__global__ void __launch_bounds__(kCommChunk)
+__global__ void __launch_bounds__(kCommThreads)
 allreduce_adam_kernel(const float* __restrict__ partial, int n_cta, long n_src,      // local partials [n_cta][n_src]
                       const float* __restrict__ extra, int n_extra,                   // appended payload (head losses)
-                      CommPeers peers, int world, int rank, uint32_t epoch, int n_pad, int n_chunks,
+                      CommPeers peers, int world, int rank, uint32_t epoch, int n_pad,
                       float* __restrict__ grad, float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
-                      float* __restrict__ extra_out, float lr_t, float b1, float b2, float eps, int* __restrict__ error) {
+                      float* __restrict__ extra_out, float lr_t, float b1, float b2, float eps, int* __restrict__ error,
+                      unsigned long long* __restrict__ trace) {
+  __shared__ float red[kCommSlices][kCommChunk];
   const int chunk = blockIdx.x;
-  const int i = chunk * kCommChunk + threadIdx.x;                 // element of the padded payload
+  const int col = threadIdx.x & (kCommChunk - 1), slice = threadIdx.x / kCommChunk;
+  const int i = chunk * kCommChunk + col;                         // element of the padded payload
   const int buf = epoch & 1u;
-  // 1. local reduction of this element
+  const bool tr = trace != nullptr && threadIdx.x == 0;          // optional phase trace: globaltimer stamps per chunk
+  if (tr) trace[chunk * 6 + 0] = globaltimer_ns();
+  asm volatile("griddepcontrol.wait;" ::: "memory");             // the producer of `partial` (programmatic dependent launch)
+  if (tr) trace[chunk * 6 + 1] = globaltimer_ns();
+  // 1. local reduction of this element: the partials are split over the slices, every load independent
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+  if (i < n_src) {
+    const float* src = partial + i;
+    int c = slice;
+    for (; c + 3 * kCommSlices < n_cta; c += 4 * kCommSlices) {
+      const float a0 = __ldcg(src + (long)c * n_src), a1 = __ldcg(src + (long)(c + kCommSlices) * n_src);
+      const float a2 = __ldcg(src + (long)(c + 2 * kCommSlices) * n_src), a3 = __ldcg(src + (long)(c + 3 * kCommSlices) * n_src);
+      g0 += a0; g1 += a1; g2 += a2; g3 += a3;
+    }
+    for (; c < n_cta; c += kCommSlices) g0 += __ldcg(src + (long)c * n_src);
+  }
+  red[slice][col] = (g0 + g1) + (g2 + g3);
+  __syncthreads();
+  if (slice != 0) return;                                         // the first kCommChunk threads own one element each
   float g = 0.f;
   if (i < n_src) {
-    float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
-    int c = 0;
-    for (; c + 4 <= n_cta; c += 4) {
-      g0 += partial[(long)c * n_src + i]; g1 += partial[(long)(c + 1) * n_src + i];
-      g2 += partial[(long)(c + 2) * n_src + i]; g3 += partial[(long)(c + 3) * n_src + i];
-    }
-    for (; c < n_cta; ++c) g0 += partial[(long)c * n_src + i];
-    g = (g0 + g1) + (g2 + g3);
+#pragma unroll
+    for (int s = 0; s < kCommSlices; ++s) g += red[s][col];
   } else if (i < n_src + n_extra) {
     g = extra[i - n_src];
   }
-  // 2. push to every rank's slot (including our own), fence, raise the flags
+  // 2. push {value, epoch} to every peer's slot for this rank
   const size_t slot_off = ((size_t)buf * world + rank) * n_pad + i;
-  for (int r = 0; r < world; ++r) peers.slots[r][slot_off] = g;
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x < world) st_release_sys(peers.flags[threadIdx.x] + (size_t)rank * n_chunks + chunk, epoch);
-  // 3. wait for this chunk of every rank
-  if (threadIdx.x < world) {
-    const uint32_t* f = peers.flags[rank] + (size_t)threadIdx.x * n_chunks + chunk;
-    long spins = 0;
-    while ((int)(ld_acquire_sys(f) - epoch) < 0) {
-      if (++spins > (1L << 24)) { *error = 1; break; }           // ~seconds: a peer is gone; never hang the GPU
-      __nanosleep(64);
-    }
-  }
-  __syncthreads();
-  const float* mine = peers.slots[rank] + (size_t)buf * world * n_pad + i;
+  for (int r = 0; r < world; ++r)
+    if (r != rank) st_ll(peers.slots[r] + slot_off, g, epoch);
+  if (tr) trace[chunk * 6 + 2] = globaltimer_ns();
+  // 3. gather every rank's element from our own slots, in rank order (identical on every rank)
+  const uint2* mine = peers.slots[rank] + (size_t)buf * world * n_pad + i;
   float s = 0.f;
-  for (int r = 0; r < world; ++r) s += __ldcg(mine + (size_t)r * n_pad);   // rank order: identical on every rank
+  for (int r = 0; r < world; ++r) {
+    float val = g;
+    if (r != rank) {
+      uint2 w = ld_ll(mine + (size_t)r * n_pad);
+      long spins = 0;
+      while (w.y != epoch) {
+        if (++spins > (1L << 24)) { *error = 1; break; }         // ~seconds: a peer is gone; never hang the GPU
+        w = ld_ll(mine + (size_t)r * n_pad);
+      }
+      val = __uint_as_float(w.x);
+    }
+    s += val;
+  }
+  if (tr) trace[chunk * 6 + 3] = globaltimer_ns();
   const float inv = 1.f / (float)world;
   if (i < n_src) {
     const float gi = s * inv;
@@ -86,6 +114,7 @@ allreduce_adam_kernel(const float* __restrict__ partial, int n_cta, long n_src, 
   } else if (i < n_src + n_extra && extra_out) {
     extra_out[i - n_src] = s * inv;
   }
+  if (tr) trace[chunk * 6 + 4] = globaltimer_ns();
 }
 
 }  // namespace v2v
@@ -97,12 +126,12 @@ struct v2v_comm {
   long n = 0;                // payload floats (parameters + extra)
   int n_pad = 0, n_chunks = 0;
   uint32_t epoch = 0;
-  float* slots = nullptr;    // local buffer: slots[2][world][n_pad] followed by flags[world][n_chunks]
-  uint32_t* flags = nullptr;
+  uint2* slots = nullptr;    // local buffer: slots[2][world][n_pad] of {value bits, epoch}
   size_t bytes = 0;
   CommPeers peers{};
   void* opened[kCommMaxWorld] = {};
   int* error_dev = nullptr;
+  unsigned long long* trace_dev = nullptr;   // optional: [n_chunks][6] globaltimer stamps of the last exchange
   bool peers_ready = false;
 };
 
@@ -113,18 +142,14 @@ extern "C" int v2v_comm_create(long n_floats, int world, int rank, v2v_comm** ou
   c->world = world; c->rank = rank; c->n = n_floats;
   c->n_chunks = (int)((n_floats + kCommChunk - 1) / kCommChunk);
   c->n_pad = c->n_chunks * kCommChunk;
-  const size_t slot_bytes = (size_t)2 * world * c->n_pad * sizeof(float);
-  const size_t flag_bytes = (size_t)world * c->n_chunks * sizeof(uint32_t);
-  c->bytes = slot_bytes + flag_bytes;
+  c->bytes = (size_t)2 * world * c->n_pad * sizeof(uint2);
   if (cudaMalloc((void**)&c->slots, c->bytes) != cudaSuccess || cudaMalloc((void**)&c->error_dev, sizeof(int)) != cudaSuccess) {
     delete c;
     return fail("v2v_comm_create: cudaMalloc failed");
   }
   cudaMemset(c->slots, 0, c->bytes);
   cudaMemset(c->error_dev, 0, sizeof(int));
-  c->flags = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(c->slots) + slot_bytes);
   c->peers.slots[rank] = c->slots;
-  c->peers.flags[rank] = c->flags;
   c->peers_ready = (world == 1);
   cudaDeviceSynchronize();
   *out = c;
@@ -153,7 +178,6 @@ extern "C" int v2v_comm_get_ipc_handle(v2v_comm* c, void* handle_out) {
 // handles: world consecutive cudaIpcMemHandle_t blobs, in rank order (ours is ignored)
 extern "C" int v2v_comm_open_peers(v2v_comm* c, const void* handles) {
   V2V_REQUIRE(c && handles, "v2v_comm_open_peers: null argument");
-  const size_t slot_bytes = (size_t)2 * c->world * c->n_pad * sizeof(float);
   for (int r = 0; r < c->world; ++r) {
     if (r == c->rank) continue;
     cudaIpcMemHandle_t h;
@@ -161,8 +185,7 @@ extern "C" int v2v_comm_open_peers(v2v_comm* c, const void* handles) {
     void* base = nullptr;
     V2V_CHECK_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
     c->opened[r] = base;
-    c->peers.slots[r] = reinterpret_cast<float*>(base);
-    c->peers.flags[r] = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(base) + slot_bytes);
+    c->peers.slots[r] = reinterpret_cast<uint2*>(base);
   }
   c->peers_ready = true;
   return 0;
@@ -179,11 +202,29 @@ extern "C" int v2v_comm_allreduce_adam(v2v_comm* c, const float* partial_dev, in
               n_src + n_extra, c->n);
   c->epoch += 1;
   const double lr_t = (double)lr * (sqrt(1.0 - pow((double)beta2, (double)t)) / (1.0 - pow((double)beta1, (double)t)));
-  allreduce_adam_kernel<<<c->n_chunks, kCommChunk, 0, (cudaStream_t)stream>>>(
-      partial_dev, n_cta, n_src, extra_dev, n_extra, c->peers, c->world, c->rank, c->epoch, c->n_pad, c->n_chunks, grad_dev,
-      p_dev, m_dev, v_dev, extra_out_dev, (float)lr_t, beta1, beta2, eps, c->error_dev);
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3(c->n_chunks);
+  lc.blockDim = dim3(kCommThreads);
+  lc.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = 1;
+  V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, allreduce_adam_kernel, partial_dev, n_cta, n_src, extra_dev, n_extra, c->peers,
+                                    c->world, c->rank, c->epoch, c->n_pad, grad_dev, p_dev, m_dev, v_dev,
+                                    extra_out_dev, (float)lr_t, beta1, beta2, eps, c->error_dev, c->trace_dev));
   return launch_status("allreduce_adam_kernel");
 }
+
+// trace_dev: device buffer of n_chunks * 6 uint64 (or null to disable); stamps per chunk: entry, producer done, pushed,
+// all ranks arrived, Adam done (globaltimer ns)
+extern "C" int v2v_comm_set_trace(v2v_comm* c, unsigned long long* trace_dev) {
+  V2V_REQUIRE(c, "v2v_comm_set_trace: null argument");
+  c->trace_dev = trace_dev;
+  return 0;
+}
+extern "C" int v2v_comm_num_chunks(v2v_comm* c) { return c ? c->n_chunks : 0; }
 
 // non-zero if a wait timed out (a peer never arrived); synchronises the stream
 extern "C" int v2v_comm_check(v2v_comm* c, void* stream) {

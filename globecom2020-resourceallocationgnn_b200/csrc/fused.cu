@@ -367,6 +367,9 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
   for (int i = tid; i < P->n_rows * RP / 4; i += kFusedThreads)      // whole arena: finite everywhere, zero row included
     reinterpret_cast<float4*>(arena)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
+  // the whole grid is resident (one CTA per SM): let the dependent reduce/Adam kernel be scheduled now, its CTAs
+  // park in griddepcontrol.wait until this grid has completed and flushed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int warp = tid >> 5, lane = tid & 31;
   int my_blk[kFusedBlkPerThread];
   float wacc[kFusedBlkPerThread][16];                  // two 4x4 weight-gradient blocks per thread (large layers)
@@ -473,29 +476,45 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
   }
 }
 
-__global__ void reduce_adam_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ grad,
-                                   float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, long n, int do_adam,
-                                   float lr_t, float b1, float b2, float eps, float gscale) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// grad[i] = sum_c partial[c][i] (+ Keras-Adam).  The sum over the n_cta per-CTA partials is latency-bound (every
+// addend is an L2 round trip), so a CTA covers only kRedCols columns and splits the partials over kRedSlices warps:
+// each thread has <= ceil(n_cta / kRedSlices) independent loads in flight, the slices meet in shared memory and are
+// added in slice order (deterministic).  Programmatic dependent launch: the prologue overlaps the producer's tail.
+constexpr int kRedCols = 32, kRedSlices = 16;
+__global__ void __launch_bounds__(kRedCols * kRedSlices)
+reduce_adam_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ grad,
+                   float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, long n, int do_adam,
+                   float lr_t, float b1, float b2, float eps, float gscale) {
+  __shared__ float red[kRedSlices][kRedCols];
+  const int col = threadIdx.x & (kRedCols - 1), slice = threadIdx.x / kRedCols;
+  const long i = (long)blockIdx.x * kRedCols + col;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
-  int c = 0;
-  for (; c + 4 <= n_cta; c += 4) {
-    g0 += partial[(long)c * n + i];
-    g1 += partial[(long)(c + 1) * n + i];
-    g2 += partial[(long)(c + 2) * n + i];
-    g3 += partial[(long)(c + 3) * n + i];
+  if (i < n) {
+    const float* src = partial + i;
+    int c = slice;
+    for (; c + 3 * kRedSlices < n_cta; c += 4 * kRedSlices) {
+      const float a0 = __ldcg(src + (long)c * n), a1 = __ldcg(src + (long)(c + kRedSlices) * n);
+      const float a2 = __ldcg(src + (long)(c + 2 * kRedSlices) * n), a3 = __ldcg(src + (long)(c + 3 * kRedSlices) * n);
+      g0 += a0; g1 += a1; g2 += a2; g3 += a3;
+    }
+    for (; c < n_cta; c += kRedSlices) g0 += __ldcg(src + (long)c * n);
   }
-  for (; c < n_cta; ++c) g0 += partial[(long)c * n + i];
-  const float g = (g0 + g1) + (g2 + g3);
-  grad[i] = g;
-  if (do_adam) {
-    const float gi = g * gscale;
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+  red[slice][col] = (g0 + g1) + (g2 + g3);
+  __syncthreads();
+  if (slice == 0 && i < n) {
+    float g = 0.f;
+#pragma unroll
+    for (int s = 0; s < kRedSlices; ++s) g += red[s][col];
+    grad[i] = g;
+    if (do_adam) {
+      const float gi = g * gscale;
+      const float mi = b1 * m[i] + (1.f - b1) * gi;
+      const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+      m[i] = mi;
+      v[i] = vi;
+      p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+    }
   }
 }
 
@@ -765,9 +784,18 @@ int fused_reduce_adam(const float* partial, int n_cta, float* grad, float* p, fl
                       float b1, float b2, float eps, float gscale, cudaStream_t st) {
   double lr_t = 0.0;
   if (t >= 1) lr_t = (double)lr * (sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
-  const int threads = 128;
-  reduce_adam_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(partial, n_cta, grad, p, m, v, n, t >= 1,
-                                                                                 (float)lr_t, b1, b2, eps, gscale);
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3((unsigned)((n + kRedCols - 1) / kRedCols));
+  lc.blockDim = dim3(kRedCols * kRedSlices);
+  lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = 1;
+  const int do_adam = t >= 1;
+  V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, reduce_adam_kernel, partial, n_cta, grad, p, m, v, n, do_adam, (float)lr_t, b1, b2,
+                                    eps, gscale));
   return launch_status("reduce_adam_kernel");
 }
 

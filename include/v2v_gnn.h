@@ -222,6 +222,10 @@ int v2v_comm_allreduce_adam(v2v_comm* c, const float* partial_dev, int n_cta, lo
                             float* m_dev, float* v_dev, float* extra_out_dev, int t, float lr, float beta1,
                             float beta2, float eps, void* stream);
 int v2v_comm_check(v2v_comm* c, void* stream);
+/* optional phase trace of the exchange kernel: trace_dev = device buffer of v2v_comm_num_chunks() * 6 uint64 (null
+ * disables); per chunk: kernel entry, producer complete, pushed + fenced, all ranks arrived, Adam done (globaltimer ns) */
+int v2v_comm_set_trace(v2v_comm* c, unsigned long long* trace_dev);
+int v2v_comm_num_chunks(v2v_comm* c);
 /* data-parallel train_dnn: local fwd + Huber + bwd, then v2v_comm_allreduce_adam; head_loss_dev receives the
  * per-head losses averaged over ranks */
 int v2v_brain_train_step_dp(v2v_brain* b, v2v_comm* comm, const float* node_dev, const float* edge_dev,
