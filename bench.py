@@ -291,12 +291,15 @@ def run_engine_arm(a):
         dt = torch.tensor([time.perf_counter() - t0], device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        h2d = B * N * (9 + 4 + N + CH) * 4
+        h2d = B * N * (9 + 4 + CH) * 4 + 2 * B * N * 4          # node, edge, targets + both adjacency bit masks
         d2h = N * 4 + 4
         e2e = {"value": world * B * k_e2e / float(dt.item()), "unit": "graphs/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": k_e2e,
-               "api": "BS.train_dnn(x_dict, y_dict, B) -> v2v_brain_train_host (numpy fp32 in, pinned staging, H2D, "
-                      "mask packing, fwd+bwd+Adam, D2H of the per-head losses)"}
+               "host_threads": int(lib.v2v_host_stage_threads()),
+               "api": "BS.train_dnn(x_dict, y_dict, B) -> v2v_brain_train_views: numpy fp32 arrays (node, edge, dense "
+                      "(B,N,N) adjacency, targets) read in place by the host worker pool (gather into pinned staging, "
+                      "adjacency bit-packed on the host), pipelined H2D, fwd+bwd+Adam, D2H of the per-head losses, one "
+                      "stream synchronisation per call"}
 
     # ---- roofline of the neighbour-aggregation kernel at the north-star point
     roof = None

@@ -29,6 +29,17 @@ class BrainConfig(C.Structure):
     ]
 
 
+class HostView(C.Structure):
+    """Mirror of ``v2v_host_view`` (include/v2v_gnn.h): a strided window of caller memory and where it lands."""
+    _fields_ = [
+        ("ptr", C.c_void_p), ("dtype", C.c_int), ("rows", C.c_long), ("cols", C.c_long),
+        ("row_stride", C.c_long), ("col_stride", C.c_long), ("dst_off", C.c_long), ("dst_row_stride", C.c_long),
+    ]
+
+
+V2V_F32, V2V_BF16, V2V_F64 = 0, 1, 2
+c_view_p = C.POINTER(HostView)
+
 # name -> (restype, argtypes).  Every symbol include/v2v_gnn.h declares is listed here;
 # tests/test_capi_symbols.py checks the two stay in sync.
 SIGNATURES = {
@@ -90,6 +101,13 @@ SIGNATURES = {
                                          c_void_p]),
     "v2v_brain_train_host": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, c_void_p,
                                        c_void_p]),
+    "v2v_brain_predict_views": (C.c_int, [c_void_p, c_view_p, C.c_int, c_view_p, C.c_int, c_view_p, C.c_int, c_view_p,
+                                          C.c_int, C.c_int, C.c_int, c_void_p, c_void_p]),
+    "v2v_brain_train_views": (C.c_int, [c_void_p, c_view_p, C.c_int, c_view_p, C.c_int, c_view_p, C.c_int, c_view_p,
+                                        C.c_int, c_view_p, C.c_int, C.c_int, c_void_p, c_void_p]),
+    "v2v_host_stage_threads": (C.c_int, []),
+    "v2v_host_gather": (C.c_int, [c_view_p, C.c_int, c_void_p, C.c_long, C.c_int, c_i32_p]),
+    "v2v_host_pack_adjacency": (C.c_int, [c_view_p, C.c_int, C.c_int, c_void_p, c_void_p, c_i32_p]),
 }
 
 

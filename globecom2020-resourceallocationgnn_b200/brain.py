@@ -391,16 +391,118 @@ class BS:
                 y.numpy()[:, k, :] = np.asarray(labels[k])
         return y
 
+    # ------------------------------------------------------------------ zero-copy input description
+    @staticmethod
+    def _view(arr, rows, cols, dst_off, dst_row_stride, keep, row_stride=None, col_stride=None):
+        """One ``v2v_host_view`` over a 2-D (rows, cols) numpy window; non-fp32/fp64 data is converted first."""
+        if arr.dtype != np.float32 and arr.dtype != np.float64:
+            arr = arr.astype(np.float32)
+        it = arr.itemsize
+        if row_stride is None:
+            rs, cs = arr.strides[0], arr.strides[1]
+            if rs % it or cs % it:
+                arr = np.ascontiguousarray(arr)
+                rs, cs = arr.strides
+            row_stride, col_stride = rs // it, cs // it
+        keep.append(arr)                                   # the C side reads the caller's memory during the call
+        return _lib.HostView(arr.__array_interface__["data"][0], _lib.V2V_F32 if it == 4 else _lib.V2V_F64, rows, cols,
+                             row_stride, col_stride, dst_off, dst_row_stride)
+
+    def _slot_views(self, data, kind, width, keep, B=None, packed_key=None):
+        """Views of one input tensor [B][N][width]: the packed extension array, or the reference's per-slot arrays."""
+        N = self.num_D2D
+        if packed_key is not None and packed_key in data:
+            a = np.asarray(data[packed_key])
+            if a.ndim != 3 or a.shape[1:] != (N, width) or (B is not None and a.shape[0] != B):
+                raise ValueError(f"{packed_key} must be (B,{N},{width}), got {a.shape}")
+            B = a.shape[0]
+            if not a.flags.c_contiguous:
+                a = np.ascontiguousarray(a)
+            return B, [self._view(a.reshape(B, N * width), B, N * width, 0, N * width, keep)]
+        views = []
+        for k in range(N):
+            key = kind.format(k + 1)
+            if key not in data:
+                raise ValueError(f"No data provided for \"{key}\". Need data for each key in the model's "
+                                 f"{'outputs' if 'Output' in key else 'inputs'}")
+            a = np.asarray(data[key])
+            if B is None:
+                B = a.shape[0]
+            if a.shape != (B, width):
+                what = "target" if "Output" in key else "input"
+                raise ValueError(f"Error when checking {what}: expected {key} to have shape ({width},) but got array "
+                                 f"with shape {a.shape[1:]}")
+            views.append(self._view(a, B, width, k * width, N * width, keep))
+        return B, views
+
+    def _input_views(self, data, keep):
+        """dict of numpy inputs (BS_brain.py:495-504, or the packed extension keys) -> ctypes view arrays."""
+        N, Dn, De, F = self.num_D2D, self.num_One_Node_Input, self.num_One_Edge_Input, self.num_Feedback
+        if not isinstance(data, dict):
+            raise ValueError("inputs must be a dict keyed by the model's input names")
+        packed = "Node_Input" in data
+        if not packed and "Adjacency_Matrix" not in data and all(f"D{k + 1}_Node_Input" in data for k in range(N)):
+            raise ValueError("No data provided for \"Adjacency_Matrix\". Need data for each key in the model's inputs")
+        B, node = self._slot_views(data, "D{}_Node_Input", Dn, keep, packed_key="Node_Input" if packed else None)
+        _, edge = self._slot_views(data, "D{}_Edge_Input", De, keep, B=B, packed_key="Edge_Input" if packed else None)
+        # neighbour inputs: the reference always feeds zeros (:478, :589); the C side notices (non-zero scan while
+        # gathering) and neither ships them nor runs that contraction
+        neigh = []
+        if packed:
+            if data.get("Neighbor_Input") is not None:
+                _, neigh = self._slot_views(data, "", F, keep, B=B, packed_key="Neighbor_Input")
+        else:
+            nbs = [data.get(f"D{k + 1}_Neighbor_Input") for k in range(N)]
+            if all(x is not None for x in nbs):
+                _, neigh = self._slot_views(data, "D{}_Neighbor_Input", F, keep, B=B)
+            elif any(x is not None for x in nbs):
+                full = {f"D{k + 1}_Neighbor_Input": (np.zeros((B, F), np.float32) if nbs[k] is None else nbs[k])
+                        for k in range(N)}
+                _, neigh = self._slot_views(full, "D{}_Neighbor_Input", F, keep, B=B)
+        if "Adjacency_Matrix" not in data:
+            raise ValueError("No data provided for \"Adjacency_Matrix\". Need data for each key in the model's inputs")
+        A = np.asarray(data["Adjacency_Matrix"])
+        if A.ndim != 3 or A.shape[0] != B:
+            raise ValueError(f"Adjacency_Matrix must be (B, N*F, N*F) or (B, N, N) with B={B}, got {A.shape}")
+        if A.dtype != np.float32 and A.dtype != np.float64:
+            A = A.astype(np.float32)
+        if not A.flags.c_contiguous:
+            A = np.ascontiguousarray(A)
+        if A.shape[1:] == (N, N):
+            adj = [self._view(A, B * N, N, 0, N, keep, row_stride=N, col_stride=1)]
+        elif A.shape[1:] == (N * F, N * F):             # kron(Adj, I_F) (:492-493): sample every F-th row and column
+            adj = [self._view(A, B * N, N, 0, N, keep, row_stride=F * N * F, col_stride=F)]
+        else:
+            raise ValueError(f"Error when checking input: expected Adjacency_Matrix to have shape ({N * F}, {N * F}) "
+                             f"but got array with shape {A.shape[1:]}")
+        return B, node, edge, neigh, adj
+
+    def _label_views(self, labels, B, keep):
+        N, CH = self.num_D2D, self.num_CH
+        if not isinstance(labels, dict):
+            labels = list(labels)
+            if len(labels) != N:
+                raise ValueError(f"expected {N} target arrays, got {len(labels)}")
+            labels = {f"D{k + 1}_Decide_Output": labels[k] for k in range(N)}
+        packed = "Decide_Output" in labels
+        _, y = self._slot_views(labels, "D{}_Decide_Output", CH, keep, B=B, packed_key="Decide_Output" if packed else None)
+        return y
+
+    @staticmethod
+    def _varr(views):
+        return (_lib.HostView * max(len(views), 1))(*views), len(views)
+
     # ------------------------------------------------------------------ the reference's methods
     def predict(self, data_test, target=False):
         """BS.predict (BS_brain.py:225-231): list of ``num_D2D`` writable arrays (B, num_CH)."""
-        B, node, edge, neigh, adj = self._pack_inputs(data_test)
+        keep = []
+        B, node, edge, neigh, adj = self._input_views(data_test, keep)
         self._ensure_capacity(B)
-        q = self._pinned("q", (B, self.num_D2D, self.num_CH))
-        _lib.check(self._lib.v2v_brain_predict_host(self._handle, ptr(node), ptr(edge), ptr(neigh), ptr(adj), B,
-                                                    int(bool(target)), ptr(q), _lib.current_stream()), ValueError)
-        qn = q.numpy()
-        return [qn[:, k, :].copy() for k in range(self.num_D2D)]
+        q = np.empty((B, self.num_D2D, self.num_CH), np.float32)
+        (na, nn), (ea, en), (ga, gn), (aa, an) = (self._varr(v) for v in (node, edge, neigh, adj))
+        _lib.check(self._lib.v2v_brain_predict_views(self._handle, na, nn, ea, en, ga, gn, aa, an, B, int(bool(target)),
+                                                     q.ctypes.data, _lib.current_stream()), ValueError)
+        return [q[:, k, :].copy() for k in range(self.num_D2D)]
 
     def predict_one_step(self, data_test, target=False):
         """BS.predict_one_step (BS_brain.py:233-235)."""
@@ -415,11 +517,35 @@ class BS:
         return self.model.fit(data_train, labels, batch_size=batch_size, epochs=1, verbose=0)
 
     def _fit(self, x, y, batch_size, epochs, shuffle):
+        bs_arg = None if batch_size is None else int(batch_size)
+        if bs_arg is not None and bs_arg < 1:
+            raise ValueError("batch_size must be >= 1")
+        if not self.data_parallel:
+            # one optimiser step per epoch on all rows (what the reference always does: :566-567, :728): the C side
+            # gathers the caller's arrays itself (csrc/host_stage.cu), nothing is repacked in Python
+            keep = []
+            B, node, edge, neigh, adj = self._input_views(x, keep)
+            if bs_arg is None or B <= bs_arg:
+                yv = self._label_views(y, B, keep)
+                self._ensure_capacity(B)
+                (na, nn), (ea, en), (ga, gn), (aa, an), (ya, yn) = (self._varr(v) for v in (node, edge, neigh, adj, yv))
+                N = self.num_D2D
+                hl = np.empty(N, np.float32)
+                hist = History()
+                keys = [f"D{k + 1}_Decide_Output_loss" for k in range(N)]
+                hist.history = {"loss": [], **{k: [] for k in keys}}
+                for ep in range(int(epochs)):
+                    _lib.check(self._lib.v2v_brain_train_views(self._handle, na, nn, ea, en, ga, gn, aa, an, ya, yn, B,
+                                                               hl.ctypes.data, _lib.current_stream()), ValueError)
+                    per_head = hl.astype(np.float64)
+                    hist.epoch.append(ep)
+                    hist.history["loss"].append(float(per_head.sum()))
+                    for k in range(N):
+                        hist.history[keys[k]].append(float(per_head[k]))
+                return hist
         B, node, edge, neigh, adj = self._pack_inputs(x)
         ylab = self._pack_labels(y, B)
         bs = B if batch_size is None else int(batch_size)
-        if bs < 1:
-            raise ValueError("batch_size must be >= 1")
         hist = History()
         N = self.num_D2D
         keys = [f"D{k + 1}_Decide_Output_loss" for k in range(N)]

@@ -8,12 +8,14 @@
 //   z  = [node | h(S-1) | a(S-1)] -> Dense 80 relu, 40 relu, 20 relu, CH linear
 // Loss: per-head mean Huber, heads summed (:86-87, :214).  Optimiser: Keras Adam (:212).
 #include <math.h>
+#include <time.h>
 #include <stdarg.h>
 #include <vector>
 
 #include <map>
 
 #include "fused.cuh"
+#include "host_stage.cuh"
 
 namespace v2v {
 
@@ -80,6 +82,8 @@ struct v2v_brain {
   uint32_t* st_in_mask = nullptr; uint32_t* st_out_mask = nullptr;
   int* st_flag = nullptr;
   int* st_flag_host = nullptr;    // pinned
+  float* pin = nullptr;           // pinned staging of the *_views entry points: node | edge | neigh | adj | y | q | head losses
+  size_t pin_node = 0, pin_edge = 0, pin_neigh = 0, pin_adj = 0, pin_y = 0, pin_q = 0, pin_hl = 0, pin_im = 0, pin_om = 0;   // offsets (floats)
   // fused whole-network path (shared weights, N <= 32, binary adjacency)
   bool fused_capable = false;
   bool fused_enabled = true;
@@ -157,6 +161,7 @@ extern "C" void v2v_brain_destroy(v2v_brain* b) {
   cudaFree(b->st_node); cudaFree(b->st_edge); cudaFree(b->st_neigh); cudaFree(b->st_adj); cudaFree(b->st_y); cudaFree(b->st_q);
   cudaFree(b->st_in_mask); cudaFree(b->st_out_mask); cudaFree(b->st_flag);
   if (b->st_flag_host) cudaFreeHost(b->st_flag_host);
+  if (b->pin) cudaFreeHost(b->pin);
   cudaFree(b->partial);
   for (auto& kv : b->fused_cache) { cudaFree(kv.second->dev); delete kv.second; }
   delete b;
@@ -209,6 +214,14 @@ extern "C" int v2v_brain_create(const v2v_brain_config* cfg, v2v_brain** out) {
   if (cudaMalloc((void**)&b->st_out_mask, rows * W * 4) != cudaSuccess) rc = 1;
   if (cudaMalloc((void**)&b->st_flag, sizeof(int)) != cudaSuccess) rc = 1;
   if (cudaMallocHost((void**)&b->st_flag_host, sizeof(int)) != cudaSuccess) rc = 1;
+  {
+    size_t o = 0;
+    auto take = [&](size_t n) { const size_t at = o; o += (n + 63) & ~(size_t)63; return at; };
+    b->pin_node = take(rows * b->Dn); b->pin_edge = take(rows * b->De); b->pin_neigh = take(rows * b->F);
+    b->pin_adj = take(rows * b->N); b->pin_y = take(rows * b->CH); b->pin_q = take(rows * b->CH); b->pin_hl = take(b->N);
+    b->pin_im = take(rows * W); b->pin_om = take(rows * W);
+    if (cudaMallocHost((void**)&b->pin, o * sizeof(float)) != cudaSuccess) rc = 1;
+  }
   if (rc) {
     std::string e = last_error();
     v2v_brain_destroy(b);
@@ -557,5 +570,143 @@ extern "C" int v2v_brain_train_host(v2v_brain* b, const float* node_host, const 
   if (head_loss_host)
     V2V_CHECK_CUDA(cudaMemcpyAsync(head_loss_host, b->head_loss, b->N * sizeof(float), cudaMemcpyDeviceToHost, st));
   V2V_CHECK_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// strided-view entry points: gather + convert on the host worker pool, pipelined H2D, one synchronisation
+// ---------------------------------------------------------------------------
+static int stage_views(v2v_brain* b, const v2v_host_view* node, int n_node, const v2v_host_view* edge, int n_edge,
+                       const v2v_host_view* neigh, int n_neigh, const v2v_host_view* adj, int n_adj,
+                       const v2v_host_view* y, int n_y, int B, bool need_out_mask, bool* weighted, bool* has_neigh,
+                       cudaStream_t st, const char* what) {
+  const long rows = (long)B * b->N;
+  V2V_REQUIRE(n_node > 0 && n_edge > 0 && n_adj > 0, "%s: node, edge and adjacency views are required", what);
+  if (int rc = host_stage_validate(node, n_node, rows * b->Dn, what)) return rc;
+  if (int rc = host_stage_validate(edge, n_edge, rows * b->De, what)) return rc;
+  if (int rc = host_stage_validate(neigh, n_neigh, rows * b->F, what)) return rc;
+  if (int rc = host_stage_validate(adj, n_adj, rows * b->N, what)) return rc;
+  if (int rc = host_stage_validate(y, n_y, rows * b->CH, what)) return rc;
+  // the workers build the bit masks themselves when the adjacency is one whole [B*N][N] view and N <= 32
+  const bool host_pack = b->N <= 32 && n_adj == 1 && adj[0].rows == rows && adj[0].cols == b->N && adj[0].dst_off == 0 &&
+                         adj[0].dst_row_stride == b->N;
+  const size_t mask_bytes = (size_t)rows * sizeof(uint32_t);
+  HostStageTensor t[5];
+  int n = 0, i_neigh = -1, i_adj = -1;
+  auto plain = [&](const v2v_host_view* v, int nv, size_t pin_off, float* dev, size_t elems) {
+    HostStageTensor T{};
+    T.views = v; T.n_views = nv; T.pinned = b->pin + pin_off; T.device = dev; T.bytes = elems * sizeof(float);
+    return T;
+  };
+  t[n++] = plain(node, n_node, b->pin_node, b->st_node, (size_t)rows * b->Dn);
+  t[n++] = plain(edge, n_edge, b->pin_edge, b->st_edge, (size_t)rows * b->De);
+  if (n_y > 0) t[n++] = plain(y, n_y, b->pin_y, b->st_y, (size_t)rows * b->CH);
+  if (n_neigh > 0) {                 // the reference always feeds zeros here (:478, :589): only non-zero data travels
+    i_neigh = n;
+    t[n] = plain(neigh, n_neigh, b->pin_neigh, b->st_neigh, (size_t)rows * b->F);
+    t[n].check = kCheckNonzero; t[n].copy_if = kFlagNonzero;
+    ++n;
+  }
+  i_adj = n;
+  t[n] = plain(adj, n_adj, b->pin_adj, b->st_adj, (size_t)rows * b->N);
+  t[n].check = kCheckBinary;
+  if (host_pack) {
+    t[n].copy_if = kFlagNonbinary;   // the dense matrix is only needed by the weighted-adjacency kernels
+    t[n].pack_N = b->N;
+    t[n].pin_in_mask = reinterpret_cast<uint32_t*>(b->pin + b->pin_im);
+    t[n].pin_out_mask = reinterpret_cast<uint32_t*>(b->pin + b->pin_om);
+    t[n].dev_in_mask = b->st_in_mask;
+    t[n].dev_out_mask = need_out_mask ? b->st_out_mask : nullptr;
+    t[n].mask_bytes = mask_bytes;
+  }
+  ++n;
+  int flags[kHostStageMaxTensors] = {0};
+  if (int rc = host_stage_run(t, n, st, flags)) return rc;
+  *weighted = (flags[i_adj] & kFlagNonbinary) != 0;
+  *has_neigh = i_neigh >= 0 && (flags[i_neigh] & kFlagNonzero) != 0;
+  if (!*weighted && !host_pack)
+    if (int rc = v2v_adj_pack_masks(b->st_adj, B, b->N, b->st_in_mask, need_out_mask ? b->st_out_mask : nullptr, nullptr, st))
+      return rc;
+  return 0;
+}
+
+extern "C" int v2v_host_stage_threads(void) { return host_stage_threads(); }
+
+// host-only pieces of the staging path, exported so that they can be checked without a device
+extern "C" int v2v_host_gather(const v2v_host_view* views, int n_views, float* dst, long dst_elems, int check, int* flags_out) {
+  V2V_REQUIRE(dst || dst_elems == 0, "v2v_host_gather: null destination");
+  if (int rc = host_stage_validate(views, n_views, dst_elems, "v2v_host_gather")) return rc;
+  HostStageTensor T{};
+  T.views = views; T.n_views = n_views; T.pinned = dst; T.check = check;
+  return host_stage_run(&T, 1, nullptr, flags_out);
+}
+
+extern "C" int v2v_host_pack_adjacency(const v2v_host_view* adj_view, int B, int N, uint32_t* in_mask, uint32_t* out_mask,
+                                       int* flags_out) {
+  V2V_REQUIRE(adj_view && in_mask && out_mask && B >= 0 && N >= 1 && N <= 32, "v2v_host_pack_adjacency: bad arguments (N <= 32)");
+  V2V_REQUIRE(adj_view->rows == (long)B * N && adj_view->cols == N, "v2v_host_pack_adjacency: the view must be [B*N][N]");
+  V2V_REQUIRE(adj_view->dtype == V2V_F32 || adj_view->dtype == V2V_F64, "v2v_host_pack_adjacency: dtype");
+  HostStageTensor T{};
+  T.views = adj_view; T.n_views = 1; T.check = kCheckBinary; T.copy_if = kFlagNonbinary;
+  T.pack_N = N; T.pin_in_mask = in_mask; T.pin_out_mask = out_mask;
+  int f = 0;
+  if (int rc = host_stage_run(&T, 1, nullptr, &f)) return rc;
+  if (flags_out) *flags_out = f;
+  return 0;
+}
+
+extern "C" int v2v_brain_predict_views(v2v_brain* b, const v2v_host_view* node, int n_node, const v2v_host_view* edge,
+                                       int n_edge, const v2v_host_view* neigh, int n_neigh, const v2v_host_view* adj,
+                                       int n_adj, int B, int target, float* q_host, void* stream) {
+  if (int rc = check_batch(b, B, "v2v_brain_predict_views")) return rc;
+  if (B == 0) return 0;
+  V2V_REQUIRE(q_host, "v2v_brain_predict_views: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  bool weighted = false, has_neigh = false;
+  if (int rc = stage_views(b, node, n_node, edge, n_edge, neigh, n_neigh, adj, n_adj, nullptr, 0, B, false, &weighted,
+                           &has_neigh, st, "v2v_brain_predict_views")) return rc;
+  if (int rc = v2v_brain_forward(b, b->st_node, b->st_edge, has_neigh ? b->st_neigh : nullptr,
+                                 weighted ? nullptr : b->st_in_mask, b->st_adj, B, target, b->st_q, stream)) return rc;
+  const size_t qb = (size_t)B * b->N * b->CH * sizeof(float);
+  V2V_CHECK_CUDA(cudaMemcpyAsync(b->pin + b->pin_q, b->st_q, qb, cudaMemcpyDeviceToHost, st));
+  V2V_CHECK_CUDA(cudaStreamSynchronize(st));
+  memcpy(q_host, b->pin + b->pin_q, qb);
+  return 0;
+}
+
+extern "C" int v2v_brain_train_views(v2v_brain* b, const v2v_host_view* node, int n_node, const v2v_host_view* edge,
+                                     int n_edge, const v2v_host_view* neigh, int n_neigh, const v2v_host_view* adj,
+                                     int n_adj, const v2v_host_view* y, int n_y, int B, float* head_loss_host,
+                                     void* stream) {
+  if (int rc = check_batch(b, B, "v2v_brain_train_views")) return rc;
+  V2V_REQUIRE(B > 0, "v2v_brain_train_views: empty batch");
+  V2V_REQUIRE(n_y > 0, "v2v_brain_train_views: target views are required");
+  cudaStream_t st = (cudaStream_t)stream;
+  bool weighted = false;
+  static const bool trace = getenv("V2V_HOST_TRACE") != nullptr;   // host-side phase timing, printed every 100 calls
+  static double acc[3] = {0, 0, 0};
+  static int calls = 0;
+  auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+  const double t0 = trace ? now() : 0;
+  bool has_neigh = false;
+  if (int rc = stage_views(b, node, n_node, edge, n_edge, neigh, n_neigh, adj, n_adj, y, n_y, B, true, &weighted, &has_neigh,
+                           st, "v2v_brain_train_views")) return rc;
+  const double t1 = trace ? now() : 0;
+  if (int rc = v2v_brain_train_step(b, b->st_node, b->st_edge, has_neigh ? b->st_neigh : nullptr,
+                                    weighted ? nullptr : b->st_in_mask, weighted ? nullptr : b->st_out_mask, b->st_adj,
+                                    b->st_y, B, b->head_loss, stream)) return rc;
+  V2V_CHECK_CUDA(cudaMemcpyAsync(b->pin + b->pin_hl, b->head_loss, b->N * sizeof(float), cudaMemcpyDeviceToHost, st));
+  const double t2 = trace ? now() : 0;
+  V2V_CHECK_CUDA(cudaStreamSynchronize(st));
+  if (trace) {
+    const double t3 = now();
+    acc[0] += t1 - t0; acc[1] += t2 - t1; acc[2] += t3 - t2;
+    if (++calls % 100 == 0) {
+      fprintf(stderr, "[v2v host trace] train_views B=%d: stage+enqueue H2D %.1f us, enqueue step %.1f us, wait %.1f us (avg of 100)\n",
+              B, acc[0] / 100, acc[1] / 100, acc[2] / 100);
+      acc[0] = acc[1] = acc[2] = 0;
+    }
+  }
+  if (head_loss_host) memcpy(head_loss_host, b->pin + b->pin_hl, b->N * sizeof(float));
   return 0;
 }

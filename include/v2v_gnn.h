@@ -37,6 +37,7 @@ extern "C" {
 
 #define V2V_F32 0
 #define V2V_BF16 1
+#define V2V_F64 2   /* host views only: the reference feeds numpy fp64 (cast to fp32 on feed, as Keras does) */
 
 #define V2V_MAX_SEG 4
 
@@ -202,6 +203,42 @@ int v2v_brain_forward_backward(v2v_brain* b, const float* node_dev, const float*
                                float* head_loss_dev, void* stream);
 /* iterations += 1; Keras-Adam on the online parameters with g * grad_scale */
 int v2v_brain_apply_adam(v2v_brain* b, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Host-buffer entry points over STRIDED VIEWS of the caller's memory: what BS.predict / BS.train_dnn receive
+ * from the reference's Agent (BS_brain.py:495-504, :664-665, :724-728) -- one array per node slot, numpy fp64,
+ * the adjacency as kron(Adj, I_F) -- without any repacking in Python.  Element (r, c) of a view is read at
+ * ptr + (r * row_stride + c * col_stride) * sizeof(dtype) and written, converted to fp32, to element
+ * dst_off + r * dst_row_stride + c of the packed staging tensor it belongs to:
+ *   node [B][N][Dn], edge [B][N][De], neighbor [B][N][F] (n_neigh = 0: all zeros, the reference's case),
+ *   adj [B][N][N] (values outside {0,1} select the weighted-adjacency kernels), y [B][N][CH].
+ * A per-slot array D{k}_Node_Input (B, Dn) is the view {rows B, cols Dn, dst_off k*Dn, dst_row_stride N*Dn};
+ * the Kronecker adjacency (B, N*F, N*F) is ONE view {rows B*N, cols N, row_stride F*N*F, col_stride F}.
+ * A persistent worker pool (V2V_HOST_THREADS, default min(8, cores/2)) gathers the views into pinned staging and
+ * each tensor's H2D copy is enqueued as soon as it is complete; the call synchronises `stream` once, at the end.
+ * q_host fp32 [B][N][CH]; head_loss_host fp32 [N]. */
+typedef struct v2v_host_view {
+  const void* ptr;
+  int dtype;                 /* V2V_F32 or V2V_F64 */
+  long rows, cols;
+  long row_stride, col_stride;   /* in elements of dtype */
+  long dst_off, dst_row_stride;  /* in floats of the staging tensor */
+} v2v_host_view;
+int v2v_brain_predict_views(v2v_brain* b, const v2v_host_view* node, int n_node, const v2v_host_view* edge, int n_edge,
+                            const v2v_host_view* neigh, int n_neigh, const v2v_host_view* adj, int n_adj, int B,
+                            int target, float* q_host, void* stream);
+int v2v_brain_train_views(v2v_brain* b, const v2v_host_view* node, int n_node, const v2v_host_view* edge, int n_edge,
+                          const v2v_host_view* neigh, int n_neigh, const v2v_host_view* adj, int n_adj,
+                          const v2v_host_view* y, int n_y, int B, float* head_loss_host, void* stream);
+int v2v_host_stage_threads(void);
+/* The host-only pieces of that path (no device involved): gather + convert views into dst (dst_elems floats) on the
+ * worker pool; check = 1 reports bit 0 of *flags_out if any element is outside {0,1}, check = 2 reports bit 1 if any
+ * element is non-zero.  v2v_host_pack_adjacency is adj_pack_kernel on the host (N <= 32), reading ONE [B*N][N] view of
+ * the caller's adjacency (dense or Kronecker): in_mask[b][m] bit n = out_mask[b][n] bit m = (adj[b][n][m] != 0);
+ * bit 0 of *flags_out reports values outside {0,1}. */
+int v2v_host_gather(const v2v_host_view* views, int n_views, float* dst, long dst_elems, int check, int* flags_out);
+int v2v_host_pack_adjacency(const v2v_host_view* adj_view, int B, int N, uint32_t* in_mask, uint32_t* out_mask,
+                            int* flags_out);
 
 /* ------------------------------------------------------------------------
  * Data parallelism (one process per GPU).  The reference has no distributed path; every batch row is an
