@@ -105,6 +105,8 @@ SIGNATURES = {
                                           C.c_int, C.c_int, C.c_int, c_void_p, c_void_p]),
     "v2v_brain_train_views": (C.c_int, [c_void_p, c_view_p, C.c_int, c_view_p, C.c_int, c_view_p, C.c_int, c_view_p,
                                         C.c_int, c_view_p, C.c_int, C.c_int, c_void_p, c_void_p]),
+    "v2v_brain_train_views_dp": (C.c_int, [c_void_p, c_void_p, c_view_p, C.c_int, c_view_p, C.c_int, c_view_p, C.c_int,
+                                           c_view_p, C.c_int, c_view_p, C.c_int, C.c_int, c_void_p, c_void_p]),
     "v2v_host_stage_threads": (C.c_int, []),
     "v2v_host_gather": (C.c_int, [c_view_p, C.c_int, c_void_p, C.c_long, C.c_int, c_i32_p]),
     "v2v_host_pack_adjacency": (C.c_int, [c_view_p, C.c_int, C.c_int, c_void_p, c_void_p, c_i32_p]),

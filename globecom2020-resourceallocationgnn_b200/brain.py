@@ -520,7 +520,7 @@ class BS:
         bs_arg = None if batch_size is None else int(batch_size)
         if bs_arg is not None and bs_arg < 1:
             raise ValueError("batch_size must be >= 1")
-        if not self.data_parallel:
+        if not self.data_parallel or self._comm is not None:
             # one optimiser step per epoch on all rows (what the reference always does: :566-567, :728): the C side
             # gathers the caller's arrays itself (csrc/host_stage.cu), nothing is repacked in Python
             keep = []
@@ -535,8 +535,13 @@ class BS:
                 keys = [f"D{k + 1}_Decide_Output_loss" for k in range(N)]
                 hist.history = {"loss": [], **{k: [] for k in keys}}
                 for ep in range(int(epochs)):
-                    _lib.check(self._lib.v2v_brain_train_views(self._handle, na, nn, ea, en, ga, gn, aa, an, ya, yn, B,
-                                                               hl.ctypes.data, _lib.current_stream()), ValueError)
+                    if self._comm is not None:       # data parallel: this rank's rows, fused NVLink exchange + Adam
+                        rc = self._lib.v2v_brain_train_views_dp(self._handle, self._comm, na, nn, ea, en, ga, gn, aa, an,
+                                                                ya, yn, B, hl.ctypes.data, _lib.current_stream())
+                    else:
+                        rc = self._lib.v2v_brain_train_views(self._handle, na, nn, ea, en, ga, gn, aa, an, ya, yn, B,
+                                                             hl.ctypes.data, _lib.current_stream())
+                    _lib.check(rc, ValueError)
                     per_head = hl.astype(np.float64)
                     hist.epoch.append(ep)
                     hist.history["loss"].append(float(per_head.sum()))

@@ -674,10 +674,10 @@ extern "C" int v2v_brain_predict_views(v2v_brain* b, const v2v_host_view* node, 
   return 0;
 }
 
-extern "C" int v2v_brain_train_views(v2v_brain* b, const v2v_host_view* node, int n_node, const v2v_host_view* edge,
-                                     int n_edge, const v2v_host_view* neigh, int n_neigh, const v2v_host_view* adj,
-                                     int n_adj, const v2v_host_view* y, int n_y, int B, float* head_loss_host,
-                                     void* stream) {
+static int train_views_impl(v2v_brain* b, struct v2v_comm* comm, const v2v_host_view* node, int n_node,
+                            const v2v_host_view* edge, int n_edge, const v2v_host_view* neigh, int n_neigh,
+                            const v2v_host_view* adj, int n_adj, const v2v_host_view* y, int n_y, int B,
+                            float* head_loss_host, void* stream) {
   if (int rc = check_batch(b, B, "v2v_brain_train_views")) return rc;
   V2V_REQUIRE(B > 0, "v2v_brain_train_views: empty batch");
   V2V_REQUIRE(n_y > 0, "v2v_brain_train_views: target views are required");
@@ -692,9 +692,12 @@ extern "C" int v2v_brain_train_views(v2v_brain* b, const v2v_host_view* node, in
   if (int rc = stage_views(b, node, n_node, edge, n_edge, neigh, n_neigh, adj, n_adj, y, n_y, B, true, &weighted, &has_neigh,
                            st, "v2v_brain_train_views")) return rc;
   const double t1 = trace ? now() : 0;
-  if (int rc = v2v_brain_train_step(b, b->st_node, b->st_edge, has_neigh ? b->st_neigh : nullptr,
-                                    weighted ? nullptr : b->st_in_mask, weighted ? nullptr : b->st_out_mask, b->st_adj,
-                                    b->st_y, B, b->head_loss, stream)) return rc;
+  const float* ng = has_neigh ? b->st_neigh : nullptr;
+  const uint32_t* im = weighted ? nullptr : b->st_in_mask;
+  const uint32_t* om = weighted ? nullptr : b->st_out_mask;
+  if (int rc = comm ? v2v_brain_train_step_dp(b, comm, b->st_node, b->st_edge, ng, im, om, b->st_adj, b->st_y, B, b->head_loss, stream)
+                    : v2v_brain_train_step(b, b->st_node, b->st_edge, ng, im, om, b->st_adj, b->st_y, B, b->head_loss, stream))
+    return rc;
   V2V_CHECK_CUDA(cudaMemcpyAsync(b->pin + b->pin_hl, b->head_loss, b->N * sizeof(float), cudaMemcpyDeviceToHost, st));
   const double t2 = trace ? now() : 0;
   V2V_CHECK_CUDA(cudaStreamSynchronize(st));
@@ -709,4 +712,20 @@ extern "C" int v2v_brain_train_views(v2v_brain* b, const v2v_host_view* node, in
   }
   if (head_loss_host) memcpy(head_loss_host, b->pin + b->pin_hl, b->N * sizeof(float));
   return 0;
+}
+
+extern "C" int v2v_brain_train_views(v2v_brain* b, const v2v_host_view* node, int n_node, const v2v_host_view* edge,
+                                     int n_edge, const v2v_host_view* neigh, int n_neigh, const v2v_host_view* adj,
+                                     int n_adj, const v2v_host_view* y, int n_y, int B, float* head_loss_host,
+                                     void* stream) {
+  return train_views_impl(b, nullptr, node, n_node, edge, n_edge, neigh, n_neigh, adj, n_adj, y, n_y, B, head_loss_host, stream);
+}
+
+// data-parallel variant: this rank's rows, gradients (and the per-head losses) exchanged by v2v_comm_allreduce_adam
+extern "C" int v2v_brain_train_views_dp(v2v_brain* b, struct v2v_comm* comm, const v2v_host_view* node, int n_node,
+                                        const v2v_host_view* edge, int n_edge, const v2v_host_view* neigh, int n_neigh,
+                                        const v2v_host_view* adj, int n_adj, const v2v_host_view* y, int n_y, int B,
+                                        float* head_loss_host, void* stream) {
+  V2V_REQUIRE(comm, "v2v_brain_train_views_dp: null communicator");
+  return train_views_impl(b, comm, node, n_node, edge, n_edge, neigh, n_neigh, adj, n_adj, y, n_y, B, head_loss_host, stream);
 }

@@ -265,6 +265,11 @@ int v2v_comm_set_trace(v2v_comm* c, unsigned long long* trace_dev);
 int v2v_comm_num_chunks(v2v_comm* c);
 /* data-parallel train_dnn: local fwd + Huber + bwd, then v2v_comm_allreduce_adam; head_loss_dev receives the
  * per-head losses averaged over ranks */
+/* the strided-view host entry point (see v2v_brain_train_views) for one rank of a data-parallel job */
+int v2v_brain_train_views_dp(v2v_brain* b, v2v_comm* comm, const v2v_host_view* node, int n_node,
+                             const v2v_host_view* edge, int n_edge, const v2v_host_view* neigh, int n_neigh,
+                             const v2v_host_view* adj, int n_adj, const v2v_host_view* y, int n_y, int B,
+                             float* head_loss_host, void* stream);
 int v2v_brain_train_step_dp(v2v_brain* b, v2v_comm* comm, const float* node_dev, const float* edge_dev,
                             const float* neighbor_dev, const uint32_t* in_mask_dev, const uint32_t* out_mask_dev,
                             const float* adj_dev, const float* y_dev, int B, float* head_loss_dev, void* stream);

@@ -41,6 +41,10 @@ def main():
             v2v._lib.check(brain._lib.v2v_comm_check(brain._comm, v2v._lib.current_stream()))
         torch.cuda.synchronize()
         results[backend] = (brain.get_flat_params(0), brain.get_flat_params(2), torch.stack(losses).cpu().numpy())
+        # a 4th step through the reference-facing host call (numpy in, per-head losses out) on this rank's rows
+        hist = brain.train_dnn({"Node_Input": node[lo:hi], "Edge_Input": edge[lo:hi], "Adjacency_Matrix": adj[lo:hi]},
+                               {"Decide_Output": y[lo:hi]}, Bl)
+        results[backend + "_host"] = (brain.get_flat_params(0), hist.history["loss"][0])
         # every rank must hold bit-identical parameters
         mine = torch.from_numpy(results[backend][0]).cuda()
         ref = mine.clone()
@@ -62,6 +66,13 @@ def main():
         gerr = np.abs(g - gs).max() / np.abs(gs).max()
         assert gerr < 5e-5, (backend, gerr)
         assert np.abs(p - ps).max() < 2e-4 and np.quantile(np.abs(p - ps), 0.9) < 2e-6, backend
+    hs = single.train_dnn({"Node_Input": node, "Edge_Input": edge, "Adjacency_Matrix": adj}, {"Decide_Output": y}, Bl * world)
+    p4 = single.get_flat_params(0)
+    for backend in ("peer", "nccl"):
+        ph, lh = results[backend + "_host"]
+        assert np.abs(ph - p4).max() < 3e-4 and np.quantile(np.abs(ph - p4), 0.9) < 3e-6, backend
+        if backend == "peer":                 # global-mean loss on every rank
+            assert abs(lh - hs.history["loss"][0]) < 1e-4 * abs(hs.history["loss"][0]), (lh, hs.history["loss"][0])
     # the peer path carries the per-head losses through the same exchange: global mean on every rank
     assert np.abs(results["peer"][2] - sl).max() < 1e-4 * np.abs(sl).max()
     dist.barrier()
