@@ -90,6 +90,9 @@ SIGNATURES = {
     "v2v_comm_allreduce_adam": (C.c_int, [c_void_p, c_void_p, C.c_int, C.c_long, c_void_p, C.c_int, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                           c_void_p]),
+    "v2v_comm_allreduce_adam_ex": (C.c_int, [c_void_p, c_void_p, C.c_int, C.c_long, C.c_long, C.c_long, c_void_p, C.c_int,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, C.c_float,
+                                             C.c_float, C.c_float, C.c_float, c_void_p]),
     "v2v_comm_check": (C.c_int, [c_void_p, c_void_p]),
     "v2v_comm_set_trace": (C.c_int, [c_void_p, c_void_p]),
     "v2v_comm_num_chunks": (C.c_int, [c_void_p]),

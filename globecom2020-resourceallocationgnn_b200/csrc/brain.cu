@@ -125,7 +125,8 @@ static int fused_get(v2v_brain* b, int B, int train, v2v_brain::FusedEntry** out
     auto* e = new v2v_brain::FusedEntry();
     if (int rc = fused_build_program(fused_shape(b), tg, train, &e->host)) { delete e; return rc; }
     if (cudaMalloc((void**)&e->dev, sizeof(FusedProgram)) != cudaSuccess) { delete e; return fail("fused path: cudaMalloc failed"); }
-    if (cudaMemcpy(e->dev, &e->host, sizeof(FusedProgram), cudaMemcpyHostToDevice) != cudaSuccess) {
+    if (cudaMemcpy(e->dev, &e->host, sizeof(FusedProgram), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaDeviceSynchronize() != cudaSuccess) {      // the kernel reads the program before its dependency wait
       cudaFree(e->dev); delete e; return fail("fused path: program upload failed");
     }
     b->fused_cache[key] = e;
@@ -233,8 +234,9 @@ extern "C" int v2v_brain_create(const v2v_brain_config* cfg, v2v_brain** out) {
     FusedProgram* probe = new FusedProgram();
     if (fused_build_program(fused_shape(b), 1, 1, probe) == 0 && fused_smem_bytes(*probe) <= 226 * 1024) {
       b->partial_ctas = sm_count();
-      if (cudaMalloc((void**)&b->partial, (size_t)b->partial_ctas * b->n_params * sizeof(float)) == cudaSuccess) {
-        cudaMemset(b->partial, 0, (size_t)b->partial_ctas * b->n_params * sizeof(float));
+      const size_t pbytes = (size_t)b->partial_ctas * fused_partial_stride((long)b->n_params) * sizeof(float);
+      if (cudaMalloc((void**)&b->partial, pbytes) == cudaSuccess) {
+        cudaMemset(b->partial, 0, pbytes);
         b->fused_capable = true;
       }
     }
@@ -416,12 +418,12 @@ extern "C" int v2v_brain_forward_backward(v2v_brain* b, const float* node, const
   if (use_fused(b, im, neigh)) {
     v2v_brain::FusedEntry* e = nullptr;
     if (int rc = fused_get(b, B, 1, &e)) return rc;
-    V2V_CHECK_CUDA(cudaMemsetAsync(hl, 0, N * sizeof(float), st));
     const int grid = fused_grid(e->host, B);
     b->last_grid = grid;
     if (int rc = fused_launch(e->host, e->dev, P, node, edge, im, om, y, nullptr, b->partial, hl, B, grid, st)) return rc;
-    if (b->defer_reduce) return 0;      // train_step fuses the reduction with Adam
-    return fused_reduce_adam(b->partial, grid, Gd, nullptr, nullptr, nullptr, (long)b->n_params, 0, 0.f, 0.f, 0.f, 0.f, 1.f, st);
+    if (b->defer_reduce) return 0;      // train_step fuses the reduction (gradient + per-head losses) with Adam
+    return fused_reduce_adam(b->partial, grid, fused_partial_stride((long)b->n_params), Gd, nullptr, nullptr, nullptr,
+                             (long)b->n_params, N, hl, 0, 0.f, 0.f, 0.f, 0.f, 1.f, st);
   }
   b->last_grid = 0;
   if (int rc = forward_impl(b, P, node, edge, neigh, im, adj, B, nullptr, stream)) return rc;
@@ -488,19 +490,19 @@ extern "C" int v2v_brain_train_step(v2v_brain* b, const float* node, const float
   if (rc) return rc;
   if (b->last_grid > 0) {             // fused path: partial reduction + Keras-Adam in one kernel
     b->iterations += 1;
-    return fused_reduce_adam(b->partial, b->last_grid, b->params[2], b->params[0], b->params[3], b->params[4],
-                             (long)b->n_params, b->iterations, b->cfg.lr, b->cfg.beta1, b->cfg.beta2, b->cfg.eps, 1.f,
-                             (cudaStream_t)stream);
+    return fused_reduce_adam(b->partial, b->last_grid, fused_partial_stride((long)b->n_params), b->params[2], b->params[0],
+                             b->params[3], b->params[4], (long)b->n_params, b->N, head_loss_dev ? head_loss_dev : b->head_loss,
+                             b->iterations, b->cfg.lr, b->cfg.beta1, b->cfg.beta2, b->cfg.eps, 1.f, (cudaStream_t)stream);
   }
   return v2v_brain_apply_adam(b, 1.f, stream);
 }
 
 // Data-parallel train step: local fwd + Huber + bwd, then ONE kernel that reduces the per-CTA partials,
 // exchanges the gradient (and the per-head losses) with all peers over NVLink and applies Adam (comm.cu).
-extern "C" int v2v_comm_allreduce_adam(struct v2v_comm* c, const float* partial_dev, int n_cta, long n_src,
-                                       const float* extra_dev, int n_extra, float* grad_dev, float* p_dev,
-                                       float* m_dev, float* v_dev, float* extra_out_dev, int t, float lr, float beta1,
-                                       float beta2, float eps, void* stream);
+extern "C" int v2v_comm_allreduce_adam_ex(struct v2v_comm* c, const float* partial_dev, int n_cta, long row_stride, long n_adam,
+                                          long n_src, const float* extra_dev, int n_extra, float* grad_dev, float* p_dev,
+                                          float* m_dev, float* v_dev, float* extra_out_dev, int t, float lr, float beta1,
+                                          float beta2, float eps, void* stream);
 
 extern "C" int v2v_brain_train_step_dp(v2v_brain* b, struct v2v_comm* comm, const float* node, const float* edge,
                                        const float* neigh, const uint32_t* in_mask, const uint32_t* out_mask,
@@ -512,10 +514,13 @@ extern "C" int v2v_brain_train_step_dp(v2v_brain* b, struct v2v_comm* comm, cons
   b->defer_reduce = false;
   if (rc) return rc;
   b->iterations += 1;
-  const bool fused = b->last_grid > 0;
-  return v2v_comm_allreduce_adam(comm, fused ? b->partial : b->params[2], fused ? b->last_grid : 1, (long)b->n_params, hl,
-                                 b->N, b->params[2], b->params[0], b->params[3], b->params[4], hl, b->iterations, b->cfg.lr,
-                                 b->cfg.beta1, b->cfg.beta2, b->cfg.eps, stream);
+  const long np = (long)b->n_params;
+  if (b->last_grid > 0)     // fused path: the per-head losses are the tail columns of the per-CTA partial rows
+    return v2v_comm_allreduce_adam_ex(comm, b->partial, b->last_grid, fused_partial_stride(np), np, np + b->N, nullptr, 0,
+                                      b->params[2], b->params[0], b->params[3], b->params[4], hl, b->iterations, b->cfg.lr,
+                                      b->cfg.beta1, b->cfg.beta2, b->cfg.eps, stream);
+  return v2v_comm_allreduce_adam_ex(comm, b->params[2], 1, np, np, np, hl, b->N, b->params[2], b->params[0], b->params[3],
+                                    b->params[4], hl, b->iterations, b->cfg.lr, b->cfg.beta1, b->cfg.beta2, b->cfg.eps, stream);
 }
 
 // ---------------------------------------------------------------------------

@@ -43,8 +43,9 @@ __device__ __forceinline__ uint2 ld_ll(const uint2* p) {
 }
 
 __global__ void __launch_bounds__(kCommThreads)
-allreduce_adam_kernel(const float* __restrict__ partial, int n_cta, long n_src,      // local partials [n_cta][n_src]
-                      const float* __restrict__ extra, int n_extra,                   // appended payload (head losses)
+allreduce_adam_kernel(const float* __restrict__ partial, int n_cta, long row_stride,  // local partials [n_cta][row_stride]
+                      long n_adam, long n_src,        // payload columns 0..n_src-1 of the rows; the first n_adam get Adam
+                      const float* __restrict__ extra, int n_extra,                   // appended payload
                       CommPeers peers, int world, int rank, uint32_t epoch, int n_pad,
                       float* __restrict__ grad, float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                       float* __restrict__ extra_out, float lr_t, float b1, float b2, float eps, int* __restrict__ error,
@@ -57,6 +58,7 @@ allreduce_adam_kernel(const float* __restrict__ partial, int n_cta, long n_src, 
   const bool tr = trace != nullptr && threadIdx.x == 0;          // optional phase trace: globaltimer stamps per chunk
   if (tr) trace[chunk * 6 + 0] = globaltimer_ns();
   asm volatile("griddepcontrol.wait;" ::: "memory");             // the producer of `partial` (programmatic dependent launch)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); // every CTA is running: the next step may queue up
   if (tr) trace[chunk * 6 + 1] = globaltimer_ns();
   // 1. local reduction of this element: the partials are split over the slices, every load independent
   float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
@@ -64,11 +66,11 @@ allreduce_adam_kernel(const float* __restrict__ partial, int n_cta, long n_src, 
     const float* src = partial + i;
     int c = slice;
     for (; c + 3 * kCommSlices < n_cta; c += 4 * kCommSlices) {
-      const float a0 = __ldcg(src + (long)c * n_src), a1 = __ldcg(src + (long)(c + kCommSlices) * n_src);
-      const float a2 = __ldcg(src + (long)(c + 2 * kCommSlices) * n_src), a3 = __ldcg(src + (long)(c + 3 * kCommSlices) * n_src);
+      const float a0 = __ldcg(src + (long)c * row_stride), a1 = __ldcg(src + (long)(c + kCommSlices) * row_stride);
+      const float a2 = __ldcg(src + (long)(c + 2 * kCommSlices) * row_stride), a3 = __ldcg(src + (long)(c + 3 * kCommSlices) * row_stride);
       g0 += a0; g1 += a1; g2 += a2; g3 += a3;
     }
-    for (; c < n_cta; c += kCommSlices) g0 += __ldcg(src + (long)c * n_src);
+    for (; c < n_cta; c += kCommSlices) g0 += __ldcg(src + (long)c * row_stride);
   }
   red[slice][col] = (g0 + g1) + (g2 + g3);
   __syncthreads();
@@ -103,7 +105,7 @@ allreduce_adam_kernel(const float* __restrict__ partial, int n_cta, long n_src, 
   }
   if (tr) trace[chunk * 6 + 3] = globaltimer_ns();
   const float inv = 1.f / (float)world;
-  if (i < n_src) {
+  if (i < n_adam) {
     const float gi = s * inv;
     grad[i] = gi;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
@@ -112,7 +114,7 @@ allreduce_adam_kernel(const float* __restrict__ partial, int n_cta, long n_src, 
     v[i] = vi;
     p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
   } else if (i < n_src + n_extra && extra_out) {
-    extra_out[i - n_src] = s * inv;
+    extra_out[i - n_adam] = s * inv;
   }
   if (tr) trace[chunk * 6 + 4] = globaltimer_ns();
 }
@@ -192,12 +194,29 @@ extern "C" int v2v_comm_open_peers(v2v_comm* c, const void* handles) {
 }
 
 // Reduce partial[n_cta][n_src] (+ extra[n_extra]) over ranks and apply Keras-Adam to p/m/v (n_src floats).
+extern "C" int v2v_comm_allreduce_adam_ex(v2v_comm* c, const float* partial_dev, int n_cta, long row_stride, long n_adam,
+                                          long n_src, const float* extra_dev, int n_extra, float* grad_dev, float* p_dev,
+                                          float* m_dev, float* v_dev, float* extra_out_dev, int t, float lr, float beta1,
+                                          float beta2, float eps, void* stream);
 extern "C" int v2v_comm_allreduce_adam(v2v_comm* c, const float* partial_dev, int n_cta, long n_src,
                                        const float* extra_dev, int n_extra, float* grad_dev, float* p_dev,
                                        float* m_dev, float* v_dev, float* extra_out_dev, int t, float lr, float beta1,
                                        float beta2, float eps, void* stream) {
+  return v2v_comm_allreduce_adam_ex(c, partial_dev, n_cta, n_src, n_src, n_src, extra_dev, n_extra, grad_dev, p_dev, m_dev,
+                                    v_dev, extra_out_dev, t, lr, beta1, beta2, eps, stream);
+}
+
+// General form: the rows of partial_dev are row_stride floats apart and carry n_src payload columns; the first n_adam
+// columns are parameters (gradient -> grad_dev, Keras-Adam on p/m/v), the remaining n_src - n_adam columns followed by
+// the n_extra floats of extra_dev are only averaged and land in extra_out_dev.
+extern "C" int v2v_comm_allreduce_adam_ex(v2v_comm* c, const float* partial_dev, int n_cta, long row_stride, long n_adam,
+                                          long n_src, const float* extra_dev, int n_extra, float* grad_dev, float* p_dev,
+                                          float* m_dev, float* v_dev, float* extra_out_dev, int t, float lr, float beta1,
+                                          float beta2, float eps, void* stream) {
   V2V_REQUIRE(c && c->peers_ready, "v2v_comm_allreduce_adam: peers not opened");
   V2V_REQUIRE(partial_dev && grad_dev && p_dev && m_dev && v_dev && n_cta >= 1 && t >= 1, "v2v_comm_allreduce_adam: bad arguments");
+  V2V_REQUIRE(n_adam >= 0 && n_adam <= n_src && n_src <= row_stride && (n_extra == 0 || extra_dev),
+              "v2v_comm_allreduce_adam: bad layout (n_adam %ld, n_src %ld, row_stride %ld)", n_adam, n_src, row_stride);
   V2V_REQUIRE(n_src + n_extra <= c->n, "v2v_comm_allreduce_adam: payload %ld exceeds the communicator's %ld floats",
               n_src + n_extra, c->n);
   c->epoch += 1;
@@ -211,7 +230,7 @@ extern "C" int v2v_comm_allreduce_adam(v2v_comm* c, const float* partial_dev, in
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = attr;
   lc.numAttrs = 1;
-  V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, allreduce_adam_kernel, partial_dev, n_cta, n_src, extra_dev, n_extra, c->peers,
+  V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, allreduce_adam_kernel, partial_dev, n_cta, row_stride, n_adam, n_src, extra_dev, n_extra, c->peers,
                                     c->world, c->rank, c->epoch, c->n_pad, grad_dev, p_dev, m_dev, v_dev,
                                     extra_out_dev, (float)lr_t, beta1, beta2, eps, c->error_dev, c->trace_dev));
   return launch_status("allreduce_adam_kernel");

@@ -352,9 +352,8 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
   float* dWs = hl_s + 32;                                   // shared weight-gradient accumulator of the small layers
   float* arena = dWs + P->n_small;
 
-  for (int i = tid; i < n_params / 4; i += kFusedThreads)
-    reinterpret_cast<float4*>(Ws)[i] = reinterpret_cast<const float4*>(params)[i];
-  for (int i = (n_params & ~3) + tid; i < n_params; i += kFusedThreads) Ws[i] = params[i];
+  // programmatic dependent launch: everything up to griddepcontrol.wait overlaps the tail of the preceding kernel
+  // (normally the previous step's reduce/Adam); it only reads the immutable program and writes shared memory
   for (int i = tid; i < n_tab; i += kFusedThreads) tab[i] = P->tab[i];
   {
     const int words = n_ops * (int)(sizeof(FusedOp) / 4);
@@ -366,6 +365,10 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
   for (int i = tid; i < P->n_small; i += kFusedThreads) dWs[i] = 0.f;
   for (int i = tid; i < P->n_rows * RP / 4; i += kFusedThreads)      // whole arena: finite everywhere, zero row included
     reinterpret_cast<float4*>(arena)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  for (int i = tid; i < n_params / 4; i += kFusedThreads)
+    reinterpret_cast<float4*>(Ws)[i] = reinterpret_cast<const float4*>(params)[i];
+  for (int i = (n_params & ~3) + tid; i < n_params; i += kFusedThreads) Ws[i] = params[i];
 
   // the whole grid is resident (one CTA per SM): let the dependent reduce/Adam kernel be scheduled now, its CTAs
   // park in griddepcontrol.wait until this grid has completed and flushed
@@ -446,7 +449,7 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
   }
 
   if (train) {
-    float* dst = partial + (size_t)blockIdx.x * n_params;
+    float* dst = partial + (size_t)blockIdx.x * (n_params + kFusedPartialTail);
 #pragma unroll
     for (int s = 0; s < kFusedBlkPerThread; ++s) {
       const int b = tid + s * kFusedThreads;
@@ -472,7 +475,7 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
         for (int i = tid; i < op.K * op.O; i += kFusedThreads) dst[op.w_off + i] = dWs[op.wt0 + i];
     }
     __syncthreads();
-    if (tid < N && hl_s[tid] != 0.f) atomicAdd(&head_loss[tid], hl_s[tid] * inv_cnt);
+    if (tid < kFusedPartialTail) dst[n_params + tid] = (tid < N) ? hl_s[tid] * inv_cnt : 0.f;   // per-head Huber sums
   }
 }
 
@@ -482,30 +485,35 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
 // added in slice order (deterministic).  Programmatic dependent launch: the prologue overlaps the producer's tail.
 constexpr int kRedCols = 32, kRedSlices = 16;
 __global__ void __launch_bounds__(kRedCols * kRedSlices)
-reduce_adam_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ grad,
-                   float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, long n, int do_adam,
-                   float lr_t, float b1, float b2, float eps, float gscale) {
+reduce_adam_kernel(const float* __restrict__ partial, int n_cta, long stride, float* __restrict__ grad,
+                   float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, long n, int n_tail,
+                   float* __restrict__ tail_out, int do_adam, float lr_t, float b1, float b2, float eps, float gscale) {
   __shared__ float red[kRedSlices][kRedCols];
   const int col = threadIdx.x & (kRedCols - 1), slice = threadIdx.x / kRedCols;
   const long i = (long)blockIdx.x * kRedCols + col;
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // every CTA is running: the next step may queue up
   float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
-  if (i < n) {
+  if (i < n + n_tail) {
     const float* src = partial + i;
     int c = slice;
     for (; c + 3 * kRedSlices < n_cta; c += 4 * kRedSlices) {
-      const float a0 = __ldcg(src + (long)c * n), a1 = __ldcg(src + (long)(c + kRedSlices) * n);
-      const float a2 = __ldcg(src + (long)(c + 2 * kRedSlices) * n), a3 = __ldcg(src + (long)(c + 3 * kRedSlices) * n);
+      const float a0 = __ldcg(src + (long)c * stride), a1 = __ldcg(src + (long)(c + kRedSlices) * stride);
+      const float a2 = __ldcg(src + (long)(c + 2 * kRedSlices) * stride), a3 = __ldcg(src + (long)(c + 3 * kRedSlices) * stride);
       g0 += a0; g1 += a1; g2 += a2; g3 += a3;
     }
-    for (; c < n_cta; c += kRedSlices) g0 += __ldcg(src + (long)c * n);
+    for (; c < n_cta; c += kRedSlices) g0 += __ldcg(src + (long)c * stride);
   }
   red[slice][col] = (g0 + g1) + (g2 + g3);
   __syncthreads();
-  if (slice == 0 && i < n) {
+  if (slice == 0 && i < n + n_tail) {
     float g = 0.f;
 #pragma unroll
     for (int s = 0; s < kRedSlices; ++s) g += red[s][col];
+    if (i >= n) {
+      if (tail_out) tail_out[i - n] = g;
+      return;
+    }
     grad[i] = g;
     if (do_adam) {
       const float gi = g * gscale;
@@ -759,8 +767,18 @@ static int fused_launch_t(const FusedProgram& ph, const FusedProgram* prog_dev, 
     V2V_CHECK_CUDA(cudaFuncSetAttribute(fused_brain_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  fused_brain_kernel<NMAX><<<grid, kFusedThreads, smem, st>>>(prog_dev, params, node, edge, in_mask, out_mask, y, q_out,
-                                                                   partial_dev, head_loss, B, inv_cnt);
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3(grid);
+  lc.blockDim = dim3(kFusedThreads);
+  lc.dynamicSmemBytes = smem;
+  lc.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = attr;
+  lc.numAttrs = 1;
+  V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, fused_brain_kernel<NMAX>, prog_dev, params, node, edge, in_mask, out_mask, y, q_out,
+                                    partial_dev, head_loss, B, inv_cnt));
   return launch_status("fused_brain_kernel");
 }
 
@@ -780,12 +798,13 @@ int fused_set_trace(long long* dev_buf) {
   return 0;
 }
 
-int fused_reduce_adam(const float* partial, int n_cta, float* grad, float* p, float* m, float* v, long n, int t, float lr,
-                      float b1, float b2, float eps, float gscale, cudaStream_t st) {
+int fused_reduce_adam(const float* partial, int n_cta, long stride, float* grad, float* p, float* m, float* v, long n,
+                      int n_tail, float* tail_out, int t, float lr, float b1, float b2, float eps, float gscale,
+                      cudaStream_t st) {
   double lr_t = 0.0;
   if (t >= 1) lr_t = (double)lr * (sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
   cudaLaunchConfig_t lc{};
-  lc.gridDim = dim3((unsigned)((n + kRedCols - 1) / kRedCols));
+  lc.gridDim = dim3((unsigned)((n + n_tail + kRedCols - 1) / kRedCols));
   lc.blockDim = dim3(kRedCols * kRedSlices);
   lc.stream = st;
   cudaLaunchAttribute attr[1];
@@ -794,8 +813,8 @@ int fused_reduce_adam(const float* partial, int n_cta, float* grad, float* p, fl
   lc.attrs = attr;
   lc.numAttrs = 1;
   const int do_adam = t >= 1;
-  V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, reduce_adam_kernel, partial, n_cta, grad, p, m, v, n, do_adam, (float)lr_t, b1, b2,
-                                    eps, gscale));
+  V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, reduce_adam_kernel, partial, n_cta, stride, grad, p, m, v, n, n_tail, tail_out,
+                                    do_adam, (float)lr_t, b1, b2, eps, gscale));
   return launch_status("reduce_adam_kernel");
 }
 

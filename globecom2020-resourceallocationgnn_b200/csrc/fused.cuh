@@ -81,8 +81,15 @@ int fused_launch(const FusedProgram& prog_host, const FusedProgram* prog_dev, co
 int fused_grid(const FusedProgram& p, int B);
 int fused_set_trace(long long* dev_buf);      // dev_buf: >= kFusedMaxOps + 1 entries, or nullptr to disable
 
-// grad[i] = sum_c partial[c][i]; optional Keras-Adam in the same pass (t >= 1).
-int fused_reduce_adam(const float* partial, int n_cta, float* grad, float* p, float* m, float* v, long n, int t, float lr,
-                      float b1, float b2, float eps, float gscale, cudaStream_t st);
+// Per-CTA partial rows are kFusedPartialTail floats longer than the parameter vector: the tail carries the CTA's
+// per-head Huber sums, so that loss and gradient leave through the same reduction (no atomics, no memset).
+constexpr int kFusedPartialTail = 32;
+inline long fused_partial_stride(long n_params) { return n_params + kFusedPartialTail; }
+
+// grad[i] = sum_c partial[c][i] for i < n; optional Keras-Adam in the same pass (t >= 1); columns n .. n + n_tail - 1
+// are summed into tail_out (the per-head losses).  partial rows are `stride` floats apart.
+int fused_reduce_adam(const float* partial, int n_cta, long stride, float* grad, float* p, float* m, float* v, long n,
+                      int n_tail, float* tail_out, int t, float lr, float b1, float b2, float eps, float gscale,
+                      cudaStream_t st);
 
 }  // namespace v2v

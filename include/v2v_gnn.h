@@ -258,6 +258,13 @@ int v2v_comm_allreduce_adam(v2v_comm* c, const float* partial_dev, int n_cta, lo
                             const float* extra_dev, int n_extra, float* grad_dev, float* p_dev,
                             float* m_dev, float* v_dev, float* extra_out_dev, int t, float lr, float beta1,
                             float beta2, float eps, void* stream);
+/* general row layout: partial rows are row_stride floats apart with n_src payload columns, of which the first n_adam are
+ * parameters (gradient + Keras-Adam); the other n_src - n_adam columns and the n_extra floats of extra_dev are only
+ * averaged over ranks into extra_out_dev (the fused brain kernel appends its per-head Huber sums to every partial row) */
+int v2v_comm_allreduce_adam_ex(v2v_comm* c, const float* partial_dev, int n_cta, long row_stride, long n_adam, long n_src,
+                               const float* extra_dev, int n_extra, float* grad_dev, float* p_dev, float* m_dev,
+                               float* v_dev, float* extra_out_dev, int t, float lr, float beta1, float beta2, float eps,
+                               void* stream);
 int v2v_comm_check(v2v_comm* c, void* stream);
 /* optional phase trace of the exchange kernel: trace_dev = device buffer of v2v_comm_num_chunks() * 6 uint64 (null
  * disables); per chunk: kernel entry, producer complete, pushed + fenced, all ranks arrived, Adam done (globaltimer ns) */
