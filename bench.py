@@ -342,6 +342,15 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "source": "B200_PROFILING.md fallback"}
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one aggregation launch, from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "agg_traffic_r01.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return d["dram_bytes_read"] + d["dram_bytes_write"]
+
+
 def agg_roofline(v2v, lib, dev, B, N, sparse, clocks):
     """Average launch duration of the aggregation kernel at (B, N, F=16, fp32), cold L2: a CUDA graph of P
     launches over P distinct (H, mask, out) sets whose total exceeds L2, replayed between two events."""
@@ -403,7 +412,7 @@ def agg_roofline(v2v, lib, dev, B, N, sparse, clocks):
                       f"> L2, so every read misses L2), {reps} replays between two CUDA events on the launch stream; the launches "
                       f"are independent (distinct buffers) and use programmatic dependent launch without the dependency wait, "
                       f"so the head of launch i+1 overlaps the tail of launch i; average = elapsed / launches",
-            "traffic": None}
+            "traffic": load_traffic()}
 
 
 def cpu_baseline_bounded(a):

@@ -76,16 +76,20 @@ class StagePool {
     }
     cv_.notify_all();
   }
-  static void drain(Job& j) {
+  // runs one work item if any is left; false when the queue is empty
+  static bool run_one(Job& j) {
     const int n = (int)j.chunks.size();
-    for (;;) {
-      const int i = j.next.fetch_add(1, std::memory_order_acq_rel);
-      if (i >= n) break;
-      const Chunk& c = j.chunks[i];
-      if (const int f = run_chunk(c)) j.flags[c.tensor].fetch_or(f, std::memory_order_relaxed);
-      j.remaining[c.tensor].fetch_sub(1, std::memory_order_acq_rel);
-      j.active.fetch_sub(1, std::memory_order_acq_rel);
-    }
+    if (j.next.load(std::memory_order_relaxed) >= n) return false;
+    const int i = j.next.fetch_add(1, std::memory_order_acq_rel);
+    if (i >= n) return false;
+    const Chunk& c = j.chunks[i];
+    if (const int f = run_chunk(c)) j.flags[c.tensor].fetch_or(f, std::memory_order_relaxed);
+    j.remaining[c.tensor].fetch_sub(1, std::memory_order_acq_rel);
+    j.active.fetch_sub(1, std::memory_order_acq_rel);
+    return true;
+  }
+  static void drain(Job& j) {
+    while (run_one(j)) {}
   }
   static void cpu_relax() {
 #if defined(__x86_64__)
@@ -101,7 +105,7 @@ class StagePool {
     if (hw <= 0) hw = 4;
     int local_world = 1;
     if (const char* e = getenv("LOCAL_WORLD_SIZE")) local_world = std::max(1, atoi(e));
-    int n = std::min(8, std::max(1, hw / (2 * local_world)));
+    int n = std::min(8, std::max(1, hw / (2 * local_world))) - (local_world > 1 ? 1 : 0);   // the caller works as well
     if (const char* e = getenv("V2V_HOST_THREADS")) n = std::max(0, std::min(64, atoi(e)));
     n_threads_ = n;
     for (int i = 0; i < n; ++i) std::thread([this] { loop(); }).detach();
@@ -271,7 +275,7 @@ int host_stage_run(const HostStageTensor* tensors, int n_tensors, cudaStream_t s
     job->remaining[t].store(cnt, std::memory_order_relaxed);
   }
   job->active.store((int)job->chunks.size(), std::memory_order_release);
-  if (pool.threads() == 0) StagePool::drain(*job); else pool.submit(job);
+  if (pool.threads() > 0) pool.submit(job);
   // enqueue each tensor's H2D as soon as it is complete (tensors are listed in the order they should travel)
   int rc = 0;
   auto h2d = [&](void* dst, const void* src, size_t bytes) {
@@ -280,7 +284,9 @@ int host_stage_run(const HostStageTensor* tensors, int n_tensors, cudaStream_t s
   };
   for (int t = 0; t < n_tensors; ++t) {
     const HostStageTensor& T = tensors[t];
-    while (job->remaining[t].load(std::memory_order_acquire) > 0) StagePool::cpu_relax();
+    // the calling thread works too (one item at a time, so a finished tensor is enqueued at most one item late)
+    while (job->remaining[t].load(std::memory_order_acquire) > 0)
+      if (!StagePool::run_one(*job)) StagePool::cpu_relax();
     const int f = job->flags[t].load(std::memory_order_acquire);
     if (flags_out) flags_out[t] = f;
     if (T.pack_N > 0) {

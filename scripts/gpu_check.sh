@@ -15,6 +15,6 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
    python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $O/ncu_launches_$TAG.log 2>&1; echo "ncu launches rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:agg_mask -c 2 -o $O/agg_full_$TAG -f \
    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_agg_$TAG.log 2>&1; echo "ncu agg rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:fused_brain -s 4 -c 1 -o $O/fused_full_$TAG -f \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:fused_brain -s 200 -c 1 -o $O/fused_full_$TAG -f \
    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_fused_$TAG.log 2>&1; echo "ncu fused rc=$?"
 ls -la $O | tail -20
