@@ -146,8 +146,9 @@ static int agg_mask_dispatch(const T* H, const uint32_t* mask, const T* addend, 
   if (F == 16 && N <= 256 && aligned && B > 0) {
     // larger graphs: set-bit / clear-bit walk (work ~ N * min(deg, N - deg)); one warp per graph tile up to
     // kAggBlockMinN nodes, one CTA per graph beyond (addend aliasing out is fine: same thread reads then writes)
-    const int rc = (N >= agg_block_min_n()) ? launch_agg_block<T>(H, mask, addend, out, B, N, !independent, st)
-                                            : launch_agg_sparse<T>(H, mask, addend, out, B, N, !independent, st);
+    int rc = (N >= agg_block_min_n()) ? launch_agg_block<T>(H, mask, addend, out, B, N, !independent, st)
+                                      : launch_agg_sparse<T>(H, mask, addend, out, B, N, !independent, st);
+    if (rc < 0 && N < agg_block_min_n()) rc = launch_agg_block<T>(H, mask, addend, out, B, N, !independent, st);
     if (rc >= 0) return rc;
   }
   const int W = ceil_div(N, 32);

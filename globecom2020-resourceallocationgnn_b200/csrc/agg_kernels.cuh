@@ -212,7 +212,66 @@ agg_mask_f16_kernel(const T* __restrict__ H, const uint32_t* __restrict__ mask,
 // bits, subtracting them from the graph's column total.  Work is O(N * min(deg, N - deg)) and the kernel stays
 // HBM-bound for both the reference-dense and the sparse variants.  (fp32 rounding differs from the sequential sum
 // by a few ulp of sum|H|, far inside the 1e-4 parity bar.)
+// The walk is the issue-bound part (ncu: 65 % issue-active, 36 M warp instructions per launch at N = 128 before this
+// form), so W = ceil(N/32) is a template parameter (mask words live in registers, loops unroll), every shared-memory
+// access uses a 32-bit shared-window address computed once per graph, and the adds are packed FADD2.
 // ---------------------------------------------------------------------------
+template <typename T> struct RowBytes { static constexpr int v = 16 * (int)sizeof(T); };
+
+__device__ __forceinline__ float4 lds_row4(uint32_t addr, const float*) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds_row4(uint32_t addr, const __nv_bfloat16*) {
+  uint2 u;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(u.x), "=r"(u.y) : "r"(addr));
+  float4 r;
+  r.x = __uint_as_float(u.x << 16);
+  r.y = __uint_as_float(u.x & 0xffff0000u);
+  r.z = __uint_as_float(u.y << 16);
+  r.w = __uint_as_float(u.y & 0xffff0000u);
+  return r;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sub4(float4& a, const float4& v) {          // a = a - v, packed
+  float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(-v.x, -v.y));
+  float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(-v.z, -v.w));
+  a.x = lo.x; a.y = lo.y; a.z = hi.x; a.w = hi.y;
+}
+
+// One target: sum of the H rows selected by its mask words (set bits, or total minus the clear bits).
+// h_addr: shared address of (row 0, this lane's feature quad); m_addr: shared address of the target's W mask words.
+template <typename T, int W>
+__device__ __forceinline__ float4 walk_target(uint32_t h_addr, uint32_t m_addr, int N, uint32_t last_valid, const float4& tot) {
+  uint32_t wds[W];
+  int cnt = 0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) { wds[w] = lds_u32(m_addr + 4 * w); cnt += __popc(wds[w]); }
+  const bool dense = 2 * cnt > N;
+  if (dense) {
+#pragma unroll
+    for (int w = 0; w < W; ++w) wds[w] = ~wds[w] & (w == W - 1 ? last_valid : 0xffffffffu);
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    uint32_t bits = wds[w];
+    const uint32_t base = h_addr + (uint32_t)(w * 32 * RowBytes<T>::v);
+    while (bits) {
+      const int n = __ffs(bits) - 1;
+      bits &= bits - 1;
+      add4(acc, lds_row4(base + (uint32_t)n * RowBytes<T>::v, (const T*)nullptr));
+    }
+  }
+  if (dense) { float4 r = tot; sub4(r, acc); return r; }
+  return acc;
+}
+
 struct AggSparseSizes {
   int h_bytes, mask_off, stage_bytes, out_bytes, warp_bytes;
 };
@@ -230,10 +289,10 @@ __host__ __device__ inline AggSparseSizes agg_sparse_sizes(int N, int W, int TG,
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 f4_sub(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 
-template <typename T, bool ADD, int WARPS>
+template <typename T, bool ADD, int WARPS, int W>
 __global__ void __launch_bounds__(WARPS * 32)
 agg_sparse_f16_kernel(const T* __restrict__ H, const uint32_t* __restrict__ mask, const T* __restrict__ addend,
-                      T* __restrict__ out, int B, int N, int W, int TG, int dep_wait) {
+                      T* __restrict__ out, int B, int N, int TG, int dep_wait) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[WARPS][kAggStages];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -253,6 +312,7 @@ agg_sparse_f16_kernel(const T* __restrict__ H, const uint32_t* __restrict__ mask
   pdl_launch_dependents();
   if (dep_wait) pdl_wait();
   const size_t graph_elems = (size_t)N * 16;
+  constexpr int RB = RowBytes<T>::v;
   auto issue = [&](int t, int s) {     // lane 0 only
     const int g0 = g_begin + t * TG;
     const int ng = min(TG, g_end - g0);
@@ -274,14 +334,13 @@ agg_sparse_f16_kernel(const T* __restrict__ H, const uint32_t* __restrict__ mask
     }
   }
   const uint32_t last_valid = (N & 31) ? ((1u << (N & 31)) - 1u) : 0xffffffffu;
+  const uint32_t out_addr = smem_u32(out_s) + (uint32_t)(c * 4 * sizeof(T));
   uint32_t phase = 0;
   int stage = 0;
   for (; tile < num_tiles; tile += WARPS) {
     const int g0 = g_begin + tile * TG;
     const int ng = min(TG, g_end - g0);
     uint8_t* st = wbase + stage * ts.stage_bytes;
-    const T* Hs = reinterpret_cast<const T*>(st);
-    const T* As = reinterpret_cast<const T*>(st + ts.h_bytes);
     uint32_t* Ms = reinterpret_cast<uint32_t*>(st + ts.mask_off);
     if (((((uint32_t)g0 * (uint32_t)(N * W) * 4u) | (uint32_t)(ng * N * W * 4)) & 15u) != 0) {
       for (int i = lane; i < ng * N * W; i += 32) Ms[i] = mask[(size_t)g0 * N * W + i];
@@ -290,37 +349,25 @@ agg_sparse_f16_kernel(const T* __restrict__ H, const uint32_t* __restrict__ mask
     mbar_wait(&bars[warp][stage], (phase >> stage) & 1u);
     if (lane == 0) bulk_wait_read<0>();            // the previous tile's store has drained out_s
     __syncwarp();
-    T* Os = reinterpret_cast<T*>(out_s);
+    const uint32_t st_addr = smem_u32(st);
     for (int g = 0; g < ng; ++g) {
-      const T* Hg = Hs + (size_t)g * graph_elems + c * 4;
-      const uint32_t* Mg = Ms + (size_t)g * N * W;
+      const uint32_t h_addr = st_addr + (uint32_t)(g * N * RB + c * 4 * (int)sizeof(T));
+      const uint32_t a_addr = h_addr + (uint32_t)ts.h_bytes;
+      const uint32_t m_addr = st_addr + (uint32_t)(ts.mask_off + g * N * W * 4);
       float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int n = tl; n < N; n += 8) tot = f4_add(tot, ld_row4(Hg + n * 16));
+      for (int n = tl; n < N; n += 8) add4(tot, lds_row4(h_addr + (uint32_t)(n * RB), (const T*)nullptr));
 #pragma unroll
       for (int off = 4; off < 32; off <<= 1) {
         tot.x += __shfl_xor_sync(0xffffffffu, tot.x, off); tot.y += __shfl_xor_sync(0xffffffffu, tot.y, off);
         tot.z += __shfl_xor_sync(0xffffffffu, tot.z, off); tot.w += __shfl_xor_sync(0xffffffffu, tot.w, off);
       }
       for (int m = tl; m < N; m += 8) {
-        const uint32_t* mm = Mg + m * W;
-        int cnt = 0;
-        for (int w = 0; w < W; ++w) cnt += __popc(mm[w]);
-        const bool dense = 2 * cnt > N;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int w = 0; w < W; ++w) {
-          uint32_t bits = mm[w];
-          if (dense) bits = ~bits & (w == W - 1 ? last_valid : 0xffffffffu);
-          while (bits) {
-            const int n = w * 32 + __ffs(bits) - 1;
-            bits &= bits - 1;
-            acc = f4_add(acc, ld_row4(Hg + n * 16));
-          }
-        }
-        float4 r = dense ? f4_sub(tot, acc) : acc;
-        if (ADD) r = f4_add(r, ld_row4(As + ((size_t)(g * N + m) * 16 + c * 4)));
-        st_row4(Os + ((size_t)(g * N + m) * 16 + c * 4), r);
+        float4 r = walk_target<T, W>(h_addr, m_addr + (uint32_t)(m * W * 4), N, last_valid, tot);
+        if (ADD) add4(r, lds_row4(a_addr + (uint32_t)(m * RB), (const T*)nullptr));
+        st_row4(reinterpret_cast<T*>(out_s) + ((size_t)(g * N + m) * 16 + c * 4), r);
       }
     }
+    (void)out_addr;
     fence_async_smem();
     __syncwarp();
     if (lane == 0) {
@@ -336,45 +383,56 @@ agg_sparse_f16_kernel(const T* __restrict__ H, const uint32_t* __restrict__ mask
 }
 
 // ---------------------------------------------------------------------------
-// Very large graphs (N > 64): one CTA per graph.  The graph's H rows and mask words arrive by bulk-async
-// copy; 256 threads = 64 targets x 4 feature quads walk the set / clear bits as above, several CTAs are
-// resident per SM so one graph's load overlaps another's walk; results go straight to global memory
-// (a warp writes 8 consecutive 64-byte rows).
+// Very large graphs (N >= 96): one CTA per graph at a time.  The graph's H rows and mask words arrive by bulk-async
+// copy into a 2-stage ring (the next graph loads while this one is walked); 256 threads = 64 targets x 4 feature quads
+// walk the set / clear bits as above; results go straight to global memory (a warp writes 8 consecutive 64-byte rows).
 // ---------------------------------------------------------------------------
-template <typename T, bool ADD>
+template <typename T, bool ADD, int W>
 __global__ void __launch_bounds__(256)
 agg_block_f16_kernel(const T* __restrict__ H, const uint32_t* __restrict__ mask, const T* __restrict__ addend,
-                     T* __restrict__ out, int B, int N, int W, int dep_wait) {
+                     T* __restrict__ out, int B, int N, int dep_wait) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar[2];
   __shared__ float4 tot_s[8][4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = tid & 3, part = tid >> 2;                         // 64 targets in flight
+  constexpr int RB = RowBytes<T>::v;
   const size_t graph_elems = (size_t)N * 16;
   const uint32_t hb = (uint32_t)(graph_elems * sizeof(T));
   const uint32_t mb = (uint32_t)(N * W * 4);
-  T* Hs = reinterpret_cast<T*>(smem_raw);
-  uint32_t* Ms = reinterpret_cast<uint32_t*>(smem_raw + hb);
-  if (tid == 0) { mbar_init(&bar, 1); fence_async_smem(); }
+  const uint32_t stage_bytes = (hb + mb + 127u) & ~127u;
+  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_async_smem(); }
   __syncthreads();
   pdl_launch_dependents();
   if (dep_wait) pdl_wait();
   const uint32_t last_valid = (N & 31) ? ((1u << (N & 31)) - 1u) : 0xffffffffu;
+  // masks whose global offset is not 16-byte aligned cannot use the bulk copy: the whole CTA copies them instead
+  const bool mask_bulk_all = (mb & 15u) == 0;       // g * mb stays 16-byte aligned for every g
+  auto issue = [&](int g, int s) {                  // thread 0 only
+    uint8_t* st = smem_raw + (size_t)s * stage_bytes;
+    mbar_arrive_expect_tx(&bar[s], hb + (mask_bulk_all ? mb : 0));
+    bulk_g2s(st, H + (size_t)g * graph_elems, hb, &bar[s]);
+    if (mask_bulk_all) bulk_g2s(st + hb, mask + (size_t)g * N * W, mb, &bar[s]);
+  };
+  int g = blockIdx.x;
+  if (tid == 0 && g < B) {
+    issue(g, 0);
+    if (g + (int)gridDim.x < B) issue(g + gridDim.x, 1);
+  }
   uint32_t phase = 0;
-  for (int g = blockIdx.x; g < B; g += gridDim.x) {
-    const bool mask_bulk = (((uint32_t)((size_t)g * N * W * 4) | mb) & 15u) == 0;
-    if (tid == 0) {
-      mbar_arrive_expect_tx(&bar, hb + (mask_bulk ? mb : 0));
-      bulk_g2s(Hs, H + (size_t)g * graph_elems, hb, &bar);
-      if (mask_bulk) bulk_g2s(Ms, mask + (size_t)g * N * W, mb, &bar);
+  int stage = 0;
+  for (; g < B; g += gridDim.x) {
+    uint8_t* st = smem_raw + (size_t)stage * stage_bytes;
+    if (!mask_bulk_all) {
+      uint32_t* Ms = reinterpret_cast<uint32_t*>(st + hb);
+      for (int i = tid; i < N * W; i += 256) Ms[i] = mask[(size_t)g * N * W + i];
+      __syncthreads();
     }
-    if (!mask_bulk) for (int i = tid; i < N * W; i += 256) Ms[i] = mask[(size_t)g * N * W + i];
-    __syncthreads();
-    mbar_wait(&bar, phase);
-    phase ^= 1u;
-    const T* Hg = Hs + c * 4;
+    mbar_wait(&bar[stage], (phase >> stage) & 1u);
+    const uint32_t h_addr = smem_u32(st) + (uint32_t)(c * 4 * sizeof(T));
+    const uint32_t m_addr = smem_u32(st) + hb;
     float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int n = part; n < N; n += 64) tot = f4_add(tot, ld_row4(Hg + n * 16));
+    for (int n = part; n < N; n += 64) add4(tot, lds_row4(h_addr + (uint32_t)(n * RB), (const T*)nullptr));
 #pragma unroll
     for (int off = 4; off < 32; off <<= 1) {
       tot.x += __shfl_xor_sync(0xffffffffu, tot.x, off); tot.y += __shfl_xor_sync(0xffffffffu, tot.y, off);
@@ -384,36 +442,27 @@ agg_block_f16_kernel(const T* __restrict__ H, const uint32_t* __restrict__ mask,
     __syncthreads();
     tot = tot_s[0][c];
 #pragma unroll
-    for (int w8 = 1; w8 < 8; ++w8) tot = f4_add(tot, tot_s[w8][c]);
+    for (int w8 = 1; w8 < 8; ++w8) add4(tot, tot_s[w8][c]);
+    const size_t obase = (size_t)g * graph_elems + c * 4;
     for (int m = part; m < N; m += 64) {
-      const uint32_t* mm = Ms + m * W;
-      int cnt = 0;
-      for (int w = 0; w < W; ++w) cnt += __popc(mm[w]);
-      const bool dense = 2 * cnt > N;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int w = 0; w < W; ++w) {
-        uint32_t bits = mm[w];
-        if (dense) bits = ~bits & (w == W - 1 ? last_valid : 0xffffffffu);
-        while (bits) {
-          const int n = w * 32 + __ffs(bits) - 1;
-          bits &= bits - 1;
-          acc = f4_add(acc, ld_row4(Hg + n * 16));
-        }
-      }
-      float4 r = dense ? f4_sub(tot, acc) : acc;
-      const size_t o = (size_t)g * graph_elems + (size_t)m * 16 + c * 4;
+      float4 r = walk_target<T, W>(h_addr, m_addr + (uint32_t)(m * W * 4), N, last_valid, tot);
+      const size_t o = obase + (size_t)m * 16;
       if (ADD) r = f4_add(r, ld_row4(addend + o));
       st_row4(out + o, r);
     }
-    __syncthreads();                     // everyone is done with Hs / Ms / tot_s before the next graph lands
+    __syncthreads();                     // everyone is done with this stage (and tot_s): refill it two graphs ahead
+    const int gn = g + 2 * (int)gridDim.x;
+    if (tid == 0 && gn < B) issue(gn, stage);
+    phase ^= (1u << stage);
+    stage ^= 1;
   }
 }
 
-template <typename T>
-static int launch_agg_block(const T* H, const uint32_t* mask, const T* addend, T* out, int B, int N, bool dep_wait,
-                            cudaStream_t st) {
-  const int W = ceil_div(N, 32);
-  const size_t smem = (size_t)N * 16 * sizeof(T) + (size_t)N * W * 4 + 128;
+template <typename T, bool ADD, int W>
+static int launch_agg_block_w(const T* H, const uint32_t* mask, const T* addend, T* out, int B, int N, bool dep_wait,
+                              cudaStream_t st) {
+  const size_t stage = (((size_t)N * 16 * sizeof(T) + (size_t)N * W * 4) + 127) & ~(size_t)127;
+  const size_t smem = 2 * stage;
   if (smem > 200 * 1024) return -1;
   const int per_sm = std::max(1, std::min(8, (int)((220 * 1024) / (smem + 1024))));
   const int grid = std::max(1, std::min(B, sm_count() * per_sm));
@@ -428,18 +477,27 @@ static int launch_agg_block(const T* H, const uint32_t* mask, const T* addend, T
   lc.attrs = attr;
   lc.numAttrs = 1;
   const int dep = dep_wait ? 1 : 0;
-  if (addend) {
-    auto k = agg_block_f16_kernel<T, true>;
-    static size_t smem_set = 0;
-    if (smem > smem_set) { V2V_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
-    V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, k, H, mask, addend, out, B, N, W, dep));
-  } else {
-    auto k = agg_block_f16_kernel<T, false>;
-    static size_t smem_set = 0;
-    if (smem > smem_set) { V2V_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
-    V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, k, H, mask, addend, out, B, N, W, dep));
-  }
+  auto k = agg_block_f16_kernel<T, ADD, W>;
+  static size_t smem_set = 0;
+  if (smem > smem_set) { V2V_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
+  V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, k, H, mask, addend, out, B, N, dep));
   return launch_status("agg_block_f16_kernel");
+}
+
+template <typename T>
+static int launch_agg_block(const T* H, const uint32_t* mask, const T* addend, T* out, int B, int N, bool dep_wait,
+                            cudaStream_t st) {
+  const int W = ceil_div(N, 32);
+#define V2V_BLOCK_CASE(WW)                                                                                         \
+  case WW:                                                                                                         \
+    return addend ? launch_agg_block_w<T, true, WW>(H, mask, addend, out, B, N, dep_wait, st)                      \
+                  : launch_agg_block_w<T, false, WW>(H, mask, addend, out, B, N, dep_wait, st);
+  switch (W) {
+    V2V_BLOCK_CASE(1) V2V_BLOCK_CASE(2) V2V_BLOCK_CASE(3) V2V_BLOCK_CASE(4)
+    V2V_BLOCK_CASE(5) V2V_BLOCK_CASE(6) V2V_BLOCK_CASE(7) V2V_BLOCK_CASE(8)
+    default: return -1;
+  }
+#undef V2V_BLOCK_CASE
 }
 
 // ---------------------------------------------------------------------------
@@ -480,15 +538,15 @@ static int launch_agg_fast(const T* H, const uint32_t* mask, const T* addend, T*
   return launch_status("agg_mask_f16_kernel");
 }
 
-template <typename T, bool ADD, int WARPS>
-static int launch_agg_sparse_t(const T* H, const uint32_t* mask, const T* addend, T* out, int B, int N, int W, int TG,
+template <typename T, bool ADD, int WARPS, int W>
+static int launch_agg_sparse_t(const T* H, const uint32_t* mask, const T* addend, T* out, int B, int N, int TG,
                                bool dep_wait, cudaStream_t st) {
   AggSparseSizes ts = agg_sparse_sizes<T>(N, W, TG, ADD);
   const size_t smem = (size_t)ts.warp_bytes * WARPS;
   const int num_tiles = ceil_div(B, TG);
   const int ctas_per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
   const int grid = std::max(1, std::min(ceil_div(num_tiles, WARPS), sm_count() * std::min(ctas_per_sm, 4)));
-  auto k = agg_sparse_f16_kernel<T, ADD, WARPS>;
+  auto k = agg_sparse_f16_kernel<T, ADD, WARPS, W>;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     V2V_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -505,30 +563,37 @@ static int launch_agg_sparse_t(const T* H, const uint32_t* mask, const T* addend
   lc.attrs = attr;
   lc.numAttrs = 1;
   const int dep = dep_wait ? 1 : 0;
-  V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, k, H, mask, addend, out, B, N, W, TG, dep));
+  V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, k, H, mask, addend, out, B, N, TG, dep));
   return launch_status("agg_sparse_f16_kernel");
 }
 
-// picks the graphs per warp tile (~4 KB of H) and the warps per CTA that fit shared memory
-template <typename T>
-static int launch_agg_sparse(const T* H, const uint32_t* mask, const T* addend, T* out, int B, int N, bool dep_wait,
-                             cudaStream_t st) {
-  const int W = ceil_div(N, 32);
+template <typename T, int W>
+static int launch_agg_sparse_w(const T* H, const uint32_t* mask, const T* addend, T* out, int B, int N, bool dep_wait,
+                               cudaStream_t st) {
   const bool add = addend != nullptr;
   int TG = std::max(1, 4096 / (N * 16 * (int)sizeof(T)));
   while (TG > 1 && ((TG * N * W * 4) & 15)) --TG;               // keep the mask span 16-byte sized for the bulk copy
   AggSparseSizes ts = agg_sparse_sizes<T>(N, W, TG, add);
   const size_t budget = 224 * 1024;
   if ((size_t)ts.warp_bytes * 8 <= budget)
-    return add ? launch_agg_sparse_t<T, true, 8>(H, mask, addend, out, B, N, W, TG, dep_wait, st)
-               : launch_agg_sparse_t<T, false, 8>(H, mask, addend, out, B, N, W, TG, dep_wait, st);
+    return add ? launch_agg_sparse_t<T, true, 8, W>(H, mask, addend, out, B, N, TG, dep_wait, st)
+               : launch_agg_sparse_t<T, false, 8, W>(H, mask, addend, out, B, N, TG, dep_wait, st);
   if ((size_t)ts.warp_bytes * 4 <= budget)
-    return add ? launch_agg_sparse_t<T, true, 4>(H, mask, addend, out, B, N, W, TG, dep_wait, st)
-               : launch_agg_sparse_t<T, false, 4>(H, mask, addend, out, B, N, W, TG, dep_wait, st);
-  if ((size_t)ts.warp_bytes * 2 <= budget)
-    return add ? launch_agg_sparse_t<T, true, 2>(H, mask, addend, out, B, N, W, TG, dep_wait, st)
-               : launch_agg_sparse_t<T, false, 2>(H, mask, addend, out, B, N, W, TG, dep_wait, st);
-  return -1;   // does not fit: caller falls back to the generic kernel
+    return add ? launch_agg_sparse_t<T, true, 4, W>(H, mask, addend, out, B, N, TG, dep_wait, st)
+               : launch_agg_sparse_t<T, false, 4, W>(H, mask, addend, out, B, N, TG, dep_wait, st);
+  return -1;   // does not fit: caller falls back
+}
+
+// warp-per-tile bit walk (graphs per warp tile ~4 KB of H); W = ceil(N/32) selects the instantiation
+template <typename T>
+static int launch_agg_sparse(const T* H, const uint32_t* mask, const T* addend, T* out, int B, int N, bool dep_wait,
+                             cudaStream_t st) {
+  switch (ceil_div(N, 32)) {
+    case 1: return launch_agg_sparse_w<T, 1>(H, mask, addend, out, B, N, dep_wait, st);
+    case 2: return launch_agg_sparse_w<T, 2>(H, mask, addend, out, B, N, dep_wait, st);
+    case 3: return launch_agg_sparse_w<T, 3>(H, mask, addend, out, B, N, dep_wait, st);
+    default: return -1;
+  }
 }
 
 template <typename T>
