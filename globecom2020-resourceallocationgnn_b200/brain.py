@@ -146,6 +146,8 @@ class BS:
                        for w in range(5)]
         if getattr(self, "_fused", 1) != 1:
             _lib.check(self._lib.v2v_brain_set_fused(h, int(self._fused)))
+        if getattr(self, "_tc_mode", None) is not None:
+            _lib.check(self._lib.v2v_brain_set_tensor_core(h, int(self._tc_mode)))
         if keep_state is not None:
             for w, t in enumerate(keep_state["bufs"]):
                 self._views[w].copy_(t)
@@ -291,6 +293,16 @@ class BS:
         mode = int(bool(enable))
         _lib.check(self._lib.v2v_brain_set_fused(self._handle, mode))
         self._fused = mode
+
+    def set_tensor_core(self, mode):
+        """predict on the tcgen05 tensor cores (3xTF32, fp32-grade): 0 never, 1 automatic (large batches), 2 always."""
+        _lib.check(self._lib.v2v_brain_set_tensor_core(self._handle, int(mode)), ValueError)
+        self._tc_mode = int(mode)
+
+    def tensor_core_info(self):
+        info = (C.c_int32 * 4)()
+        _lib.check(self._lib.v2v_brain_tensor_core_info(self._handle, info))
+        return dict(zip(("capable", "mode", "graphs_per_tile", "smem_bytes"), list(info)))
 
     def fused_info(self, B, train=True):
         info = (C.c_int * 8)()

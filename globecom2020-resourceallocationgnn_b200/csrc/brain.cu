@@ -16,6 +16,7 @@
 
 #include "fused.cuh"
 #include "host_stage.cuh"
+#include "tc_forward.cuh"
 
 namespace v2v {
 
@@ -96,6 +97,11 @@ struct v2v_brain {
   int partial_ctas = 0;
   int last_grid = 0;                            // grid of the last fused train launch (0: layered path ran)
   bool defer_reduce = false;
+  // tensor-core (tcgen05) forward of the shared-weight brain
+  bool tc_capable = false;
+  int tc_mode = 1;                              // 0: off, 1: auto (batches with >= 8 tiles per SM), 2: always
+  TcPlan tc_plan;
+  TcPlan* tc_plan_dev = nullptr;
 };
 
 static FusedShape fused_shape(const v2v_brain* b) {
@@ -164,6 +170,7 @@ extern "C" void v2v_brain_destroy(v2v_brain* b) {
   if (b->st_flag_host) cudaFreeHost(b->st_flag_host);
   if (b->pin) cudaFreeHost(b->pin);
   cudaFree(b->partial);
+  cudaFree(b->tc_plan_dev);
   for (auto& kv : b->fused_cache) { cudaFree(kv.second->dev); delete kv.second; }
   delete b;
 }
@@ -242,7 +249,19 @@ extern "C" int v2v_brain_create(const v2v_brain_config* cfg, v2v_brain** out) {
     }
     delete probe;
     last_error().clear();
+    // tensor-core forward plan (predict at large batch)
+    TcShape ts;
+    ts.N = b->N; ts.Dn = b->Dn; ts.De = b->De; ts.F = b->F; ts.CH = b->CH; ts.S = b->S;
+    ts.H1 = cfg->hidden[0]; ts.H2 = cfg->hidden[1]; ts.H3 = cfg->hidden[2];
+    ts.w_off = b->lw.data(); ts.b_off = b->lb.data();
+    if (tc_build_plan(ts, &b->tc_plan) == 0 && cudaMalloc((void**)&b->tc_plan_dev, sizeof(TcPlan)) == cudaSuccess &&
+        cudaMemcpy(b->tc_plan_dev, &b->tc_plan, sizeof(TcPlan), cudaMemcpyHostToDevice) == cudaSuccess) {
+      b->tc_capable = true;
+    }
+    last_error().clear();
+    if (const char* e = getenv("V2V_TENSOR_CORE")) b->tc_mode = atoi(e);
   }
+  cudaDeviceSynchronize();
   *out = b;
   return 0;
 }
@@ -389,6 +408,10 @@ extern "C" int v2v_brain_forward(v2v_brain* b, const float* node_dev, const floa
   if (B == 0) return 0;
   V2V_REQUIRE(node_dev && edge_dev && q_dev, "v2v_brain_forward: null pointer");
   V2V_REQUIRE(in_mask_dev || adj_dev, "v2v_brain_forward: need in_mask or adj");
+  if (b->tc_capable && b->tc_mode > 0 && b->fused_enabled && in_mask_dev && !neighbor_dev &&
+      (b->tc_mode >= 2 || ceil_div(B, b->tc_plan.TG) >= 8 * sm_count()))
+    return tc_forward_launch(b->tc_plan, b->tc_plan_dev, b->params[target ? 1 : 0], node_dev, edge_dev, in_mask_dev, q_dev, B,
+                             (cudaStream_t)stream);
   if (use_fused(b, in_mask_dev, neighbor_dev)) {
     v2v_brain::FusedEntry* e = nullptr;
     if (int rc = fused_get(b, B, 0, &e)) return rc;
@@ -636,6 +659,30 @@ static int stage_views(v2v_brain* b, const v2v_host_view* node, int n_node, cons
 }
 
 extern "C" int v2v_host_stage_threads(void) { return host_stage_threads(); }
+
+// mode 0: never, 1: automatic (batches that give every SM at least eight 128-row tiles), 2: whenever the brain is capable
+extern "C" int v2v_brain_set_tensor_core(v2v_brain* b, int mode) {
+  V2V_REQUIRE(b, "v2v_brain_set_tensor_core: null brain");
+  V2V_REQUIRE(mode >= 0 && mode <= 2, "v2v_brain_set_tensor_core: mode %d outside [0,2]", mode);
+  V2V_REQUIRE(mode == 0 || b->tc_capable, "v2v_brain_set_tensor_core: this configuration has no tensor-core forward "
+              "(needs shared weights, N <= 32, feedback width a multiple of 8)");
+  b->tc_mode = mode;
+  return 0;
+}
+// debugging aid: runs the tensor-core forward and dumps the raw accumulator [128][Npad] of one layer of the first tile
+extern "C" int v2v_brain_tc_debug(v2v_brain* b, const float* node, const float* edge, const uint32_t* in_mask, int B,
+                                  int layer, float* q_dev, float* dbg_dev, int* npad_out, void* stream) {
+  V2V_REQUIRE(b && b->tc_capable && layer >= 0 && layer < b->tc_plan.n_layers, "v2v_brain_tc_debug: bad arguments");
+  if (npad_out) *npad_out = b->tc_plan.layers[layer].Npad;
+  return tc_forward_launch(b->tc_plan, b->tc_plan_dev, b->params[0], node, edge, in_mask, q_dev, B, (cudaStream_t)stream,
+                           dbg_dev, layer);
+}
+extern "C" int v2v_brain_tensor_core_info(const v2v_brain* b, int* info4) {
+  V2V_REQUIRE(b && info4, "v2v_brain_tensor_core_info: null argument");
+  info4[0] = b->tc_capable ? 1 : 0; info4[1] = b->tc_mode; info4[2] = b->tc_capable ? b->tc_plan.TG : 0;
+  info4[3] = b->tc_capable ? b->tc_plan.smem_bytes : 0;
+  return 0;
+}
 
 // host-only pieces of the staging path, exported so that they can be checked without a device
 extern "C" int v2v_host_gather(const v2v_host_view* views, int n_views, float* dst, long dst_elems, int check, int* flags_out) {

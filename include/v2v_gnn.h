@@ -171,6 +171,15 @@ int v2v_brain_set_fused(v2v_brain* b, int enable);
 /* Describes the fused program for a batch of B graphs: info8 = {capable, graphs per tile, arena
  * feature rows, shared-memory bytes, phases, weight-gradient blocks, bias slots, table entries}. */
 int v2v_brain_fused_info(v2v_brain* b, int B, int train, int* info8);
+/* predict on the tensor cores (csrc/tc_forward.cu: tcgen05.mma kind::tf32, 3 passes per contraction = fp32-grade
+ * products, accumulators in TMEM): mode 0 never, 1 automatic (default: batches that give every SM >= 8 tiles of 128 node
+ * rows), 2 whenever the brain is capable (shared weights, N <= 32, binary adjacency, zero neighbour input).
+ * info4 = {capable, mode, graphs per tile, shared-memory bytes}.  Environment override at creation: V2V_TENSOR_CORE. */
+int v2v_brain_set_tensor_core(v2v_brain* b, int mode);
+int v2v_brain_tensor_core_info(const v2v_brain* b, int* info4);
+/* debugging aid: tensor-core forward that also dumps the raw fp32 accumulator [128][Npad] of `layer` for the first tile */
+int v2v_brain_tc_debug(v2v_brain* b, const float* node_dev, const float* edge_dev, const uint32_t* in_mask_dev, int B,
+                       int layer, float* q_dev, float* dbg_dev, int* npad_out, void* stream);
 /* Profiling aid: lane 0 of every warp of CTA 0 writes clock64() into dev_buf[(phase*12 + warp)*2 + {0: work
  * done, 1: barrier released}] for its first tile (dev_buf >= 49*12*2 entries, device memory); NULL disables. */
 int v2v_fused_set_trace(long long* dev_buf);
