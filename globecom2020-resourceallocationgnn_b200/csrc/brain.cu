@@ -672,8 +672,8 @@ extern "C" int v2v_brain_set_tensor_core(v2v_brain* b, int mode) {
 // debugging aid: runs the tensor-core forward and dumps the raw accumulator [128][Npad] of one layer of the first tile
 extern "C" int v2v_brain_tc_debug(v2v_brain* b, const float* node, const float* edge, const uint32_t* in_mask, int B,
                                   int layer, float* q_dev, float* dbg_dev, int* npad_out, void* stream) {
-  V2V_REQUIRE(b && b->tc_capable && layer >= 0 && layer < b->tc_plan.n_layers, "v2v_brain_tc_debug: bad arguments");
-  if (npad_out) *npad_out = b->tc_plan.layers[layer].Npad;
+  V2V_REQUIRE(b && b->tc_capable && layer >= -2 && layer < b->tc_plan.n_layers, "v2v_brain_tc_debug: bad arguments");
+  if (npad_out) *npad_out = layer >= 0 ? b->tc_plan.layers[layer].Npad : b->tc_plan.n_layers;   // -2: phase trace (clock64 stamps)
   return tc_forward_launch(b->tc_plan, b->tc_plan_dev, b->params[0], node, edge, in_mask, q_dev, B, (cudaStream_t)stream,
                            dbg_dev, layer);
 }

@@ -13,8 +13,10 @@
 //     x = hi + lo into two TF32 values and every k-step issues THREE tcgen05.mma.kind::tf32 into the same fp32 TMEM
 //     accumulator: hi*hi + hi*lo + lo*hi (the dropped lo*lo term is 2^-22 relative);
 //   * one elected thread issues the MMAs and a tcgen05.commit on an mbarrier; all 8 warps then read the accumulator
-//     with tcgen05.ld (warp w: lanes 32*(w%4).., column half w/4), add the bias, apply ReLU and write the NEXT
-//     layer's operand planes (already split into hi/lo) -- activations of the MLP never exist in fp32 anywhere;
+//     with tcgen05.ld (warp w: lanes 32*(w%4).., column half w/4; all loads in flight, one wait), add the bias, apply
+//     ReLU and write the NEXT layer's operand planes already split into hi/lo -- there is no separate split pass:
+//     the tile loader, the combine epilogue and the aggregation all emit hi/lo planes directly, and the next tile's
+//     inputs are prefetched into registers while the current tile computes;
 //   * the neighbour aggregation between the combine stages is the same register gather-reduce over bit masks as in the
 //     FP32 kernel, on the plane layout (zero HBM traffic).
 // Used for predict at batch sizes that give every SM at least two tiles; smaller batches stay on the FP32-pipe fused
@@ -29,7 +31,7 @@ namespace {
 
 constexpr int kPlaneBytes = kTcRows * 16;      // one plane: 128 rows x 4 floats
 constexpr int kPlaneFloats = kTcRows * 4;
-constexpr uint32_t kTmemCols = 128;            // accumulator columns (power of two >= the widest layer, 80)
+constexpr uint32_t kTmemCols = 256;            // accumulator columns (power of two >= 2 x the widest layer, 2 x 80)
 
 // ---- tcgen05 primitives (inline PTX, sm_100a) ------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {          // one full warp
@@ -78,11 +80,34 @@ __device__ __forceinline__ float tf32_rn(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+// x = hi + lo with hi the TF32 truncation of x (one LOP) and lo = x - hi exactly (one FADD); the tensor core reads only
+// the upper 19 bits of lo, so hi + tf32(lo) carries >= 21 significand bits.  (cvt.rna.tf32 is a quarter-rate
+// conversion and dominated the epilogues.)
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 __device__ __forceinline__ void split4(const float4& x, float4& hi, float4& lo) {
-  hi.x = tf32_rn(x.x); hi.y = tf32_rn(x.y); hi.z = tf32_rn(x.z); hi.w = tf32_rn(x.w);
-  lo.x = tf32_rn(x.x - hi.x); lo.y = tf32_rn(x.y - hi.y); lo.z = tf32_rn(x.z - hi.z); lo.w = tf32_rn(x.w - hi.w);
+  hi.x = tf32_hi(x.x); hi.y = tf32_hi(x.y); hi.z = tf32_hi(x.z); hi.w = tf32_hi(x.w);
+  lo.x = x.x - hi.x; lo.y = x.y - hi.y; lo.z = x.z - hi.z; lo.w = x.w - hi.w;
 }
 
+// issue a TMEM load of 8 columns without waiting (pair with tc_wait_ld before the registers are read)
+__device__ __forceinline__ void tc_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void padd4(float4& a, const float4& v) {
+  float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(v.x, v.y));
+  float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(v.z, v.w));
+  a.x = lo.x; a.y = lo.y; a.z = hi.x; a.w = hi.y;
+}
+
+constexpr int kTcMaxInItems = 2;       // x0 items (row, plane) per thread: x_planes * 128 / 256
+
+// Shared-memory operand planes of a tile ("stage", hi and lo copies): [h (F/4) | aggregated (F/4) | x0 (x_planes)] for
+// the combine layers and the first MLP layer, then re-used as [previous layer's output] for the rest of the MLP.
+// Nothing is ever split in a separate pass: the tile loader writes x0 as hi/lo, the combine epilogue writes h as fp32
+// (for the aggregation) and as hi/lo, the aggregation writes its result as hi/lo.
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_forward_kernel(const TcPlan* __restrict__ P, const float* __restrict__ params, const float* __restrict__ node,
                   const float* __restrict__ edge, const uint32_t* __restrict__ in_mask, float* __restrict__ q_out, int B,
@@ -94,177 +119,234 @@ tc_forward_kernel(const TcPlan* __restrict__ P, const float* __restrict__ params
   const int N = P->N, TG = P->TG, Dn = P->Dn, De = P->De, CH = P->CH, XP = P->x_planes, dn_pad = P->dn_pad;
   const int FP = P->F >> 2;                                   // planes of h / agg
   const int n_layers = P->n_layers;
+  const int SP = P->stage_planes;
 
   float* Wsm = reinterpret_cast<float*>(smem);
   float* bias_s = Wsm + P->w_floats;
-  float* xs = bias_s + P->bias_floats;                        // x0 planes (fp32)
-  float* hs = xs + XP * kPlaneFloats;                         // h planes (fp32)
-  float* as = hs + FP * kPlaneFloats;                         // aggregated planes (fp32)
-  float* stage_hi = as + FP * kPlaneFloats;                   // current MMA operand, hi / lo planes
-  float* stage_lo = stage_hi + P->stage_planes * kPlaneFloats;
-  uint32_t* mask_s = reinterpret_cast<uint32_t*>(stage_lo + P->stage_planes * kPlaneFloats);
+  float* hs = bias_s + P->bias_floats;                        // h planes (fp32, read by the aggregation)
+  float* stage_hi = hs + FP * kPlaneFloats;                   // MMA operand planes, hi / lo
+  float* stage_lo = stage_hi + SP * kPlaneFloats;
+  uint32_t* mask_s = reinterpret_cast<uint32_t*>(stage_lo + SP * kPlaneFloats);
 
   if (tid == 0) {
     mbar_init(&bar, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, kTmemCols);
+  for (int i = tid; i < 2 * SP * kPlaneFloats; i += kTcThreads) stage_hi[i] = 0.f;   // finite everywhere (padding rows)
   asm volatile("griddepcontrol.wait;" ::: "memory");          // parameters may come from the preceding optimiser kernel
   // ---- weights: parameters -> hi/lo planes over k (K-major B operand), biases zero-padded
   for (int l = 0; l < n_layers; ++l) {
     const TcLayer& L = P->layers[l];
     const int Kpad = L.Kpad, Npad = L.Npad, No = L.N;
-    float* Wh = Wsm + L.w_off;
-    float* Wl = Wh + Kpad * Npad;
+    float* Wc = Wsm + L.w_off;          // k-plane kc: rows [0, Npad) = hi(W[k][o]), rows [Npad, 2 Npad) = lo, 4 k's per row
     for (int idx = tid; idx < Kpad * Npad; idx += kTcThreads) {
       const int o = idx % Npad, k = idx / Npad;               // consecutive threads read consecutive o of one W row
-      const int row = L.kmap[k];
-      const float w = (row >= 0 && o < No) ? params[L.pw_off + row * No + o] : 0.f;
+      const int wrow = L.kmap[k];
+      const float w = (wrow >= 0 && o < No) ? params[L.pw_off + wrow * No + o] : 0.f;
       const float h = tf32_rn(w);
-      const int at = (k >> 2) * (Npad * 4) + o * 4 + (k & 3);
-      Wh[at] = h;
-      Wl[at] = tf32_rn(w - h);
+      const int at = (k >> 2) * (2 * Npad * 4) + o * 4 + (k & 3);
+      Wc[at] = h;
+      Wc[at + Npad * 4] = tf32_rn(w - h);
     }
     for (int o = tid; o < Npad; o += kTcThreads) bias_s[L.bias_off + o] = (o < No) ? params[L.pb_off + o] : 0.f;
   }
-  for (int i = tid; i < FP * kPlaneFloats; i += kTcThreads) as[i] = 0.f;   // rows past the tile's last node stay zero
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  const int q4 = warp & 3, half = warp >> 2;
+  const int row = q4 * 32 + lane;                             // this thread's accumulator lane = tile row
+  const int num_tiles = (B + TG - 1) / TG;
+  const int MS = (N + 1) >> 1;                                // aggregation: two targets per item
+  const int x_plane0 = 2 * FP;                                // x0 lives behind h and agg in the operand planes
+  uint32_t phase = 0;
+
+  // ---- input prefetch: the next tile's node / edge features and mask words wait in registers
+  float xin[kTcMaxInItems][4];
+  uint32_t min_ = 0u;
+  auto fetch = [&](int tile) {
+    const int g0 = tile * TG;
+    const int R = (tile < num_tiles) ? min(TG, B - g0) * N : 0;
+#pragma unroll
+    for (int it = 0; it < kTcMaxInItems; ++it) {
+      const int idx = tid + it * kTcThreads;
+      const int r = idx & (kTcRows - 1), pl = idx >> 7;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xin[it][j] = 0.f;
+      if (pl < XP && r < R) {
+        const size_t gr = (size_t)g0 * N + r;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int f = pl * 4 + j;
+          if (f < Dn) xin[it][j] = __ldg(node + gr * Dn + f);
+          else if (f >= dn_pad && f - dn_pad < De) xin[it][j] = __ldg(edge + gr * De + (f - dn_pad));
+        }
+      }
+    }
+    min_ = (tid < TG * N && tid < R) ? __ldg(in_mask + (size_t)g0 * N + tid) : 0u;
+  };
+  fetch(blockIdx.x);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-
-  const int q4 = warp & 3, half = warp >> 2;
-  const int row = q4 * 32 + lane;                             // this thread's accumulator lane = tile row
   const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16);
-  const int num_tiles = (B + TG - 1) / TG;
-  const int MS = (N + 1) >> 1;                                // aggregation: two targets per item
-  uint32_t phase = 0;
 
+  // profiling aid (dbg_layer == -2): thread 0 of CTA 0 stamps clock64() at the phase boundaries of its second tile
+  long long* trace = (dbg && dbg_layer == -2 && blockIdx.x == 0 && tid == 0) ? reinterpret_cast<long long*>(dbg) : nullptr;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    long long* tr = (trace && tile == blockIdx.x + gridDim.x) ? trace : nullptr;
+    if (tr) tr[0] = clock64();
     const int g0 = tile * TG;
     const int ng = min(TG, B - g0);
     const int R = ng * N;
-    // ---- inputs -> x0 planes [node (padded) | edge (padded)], masks
-    for (int idx = tid; idx < XP * kTcRows; idx += kTcThreads) {
-      const int r = idx & (kTcRows - 1), pl = idx >> 7;
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
-      if (r < R) {
-        const size_t gr = (size_t)g0 * N + r;
+    // ---- prefetched inputs -> x0 operand planes (hi / lo), masks; then start fetching the next tile
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int f = pl * 4 + j;
-          if (f < Dn) v[j] = node[gr * Dn + f];
-          else if (f >= dn_pad && f - dn_pad < De) v[j] = edge[gr * De + (f - dn_pad)];
-        }
+    for (int it = 0; it < kTcMaxInItems; ++it) {
+      const int idx = tid + it * kTcThreads;
+      const int r = idx & (kTcRows - 1), pl = idx >> 7;
+      if (pl < XP) {
+        float4 hi, lo;
+        split4(make_float4(xin[it][0], xin[it][1], xin[it][2], xin[it][3]), hi, lo);
+        *reinterpret_cast<float4*>(stage_hi + (x_plane0 + pl) * kPlaneFloats + r * 4) = hi;
+        *reinterpret_cast<float4*>(stage_lo + (x_plane0 + pl) * kPlaneFloats + r * 4) = lo;
       }
-      *reinterpret_cast<float4*>(xs + pl * kPlaneFloats + r * 4) = make_float4(v[0], v[1], v[2], v[3]);
     }
-    for (int i = tid; i < TG * N; i += kTcThreads) mask_s[i] = (i < R) ? in_mask[(size_t)g0 * N + i] : 0u;
-    __syncthreads();
+    if (tid < TG * N) mask_s[tid] = min_;
+    fetch(tile + gridDim.x);
+    if (tr) tr[1] = clock64();
 
     for (int l = 0; l < n_layers; ++l) {
       const TcLayer& L = P->layers[l];
       const int Kpad = L.Kpad, Npad = L.Npad;
-      // ---- operand planes for the combine layers: split the fp32 planes into hi / lo
-      if (L.a_src != 2) {
-        const int np = Kpad >> 2;
-        for (int idx = tid; idx < np * kTcRows; idx += kTcThreads) {
-          const int r = idx & (kTcRows - 1), pl = idx >> 7;
-          const float* src;
-          if (L.a_src == 0) src = xs + pl * kPlaneFloats;
-          else src = pl < FP ? hs + pl * kPlaneFloats : (pl < 2 * FP ? as + (pl - FP) * kPlaneFloats : xs + (pl - 2 * FP) * kPlaneFloats);
-          const float4 x = *reinterpret_cast<const float4*>(src + r * 4);
-          float4 hi, lo;
-          split4(x, hi, lo);
-          *reinterpret_cast<float4*>(stage_hi + pl * kPlaneFloats + r * 4) = hi;
-          *reinterpret_cast<float4*>(stage_lo + pl * kPlaneFloats + r * 4) = lo;
-        }
-      }
       fence_async_smem();                 // generic-proxy writes of the operand planes -> visible to the tensor core
       tc_fence_before();                  // the previous epilogue's TMEM reads are ordered before the barrier
       __syncthreads();
+      if (tr) tr[2 + 4 * l] = clock64();
       // ---- one thread issues the 3xTF32 MMAs of the layer and commits them to the mbarrier
       if (tid == 0) {
         tc_fence_after();
-        const uint32_t idesc = umma_idesc_tf32(Npad);
-        const uint32_t a_hi = smem_u32(stage_hi), a_lo = smem_u32(stage_lo);
-        const uint32_t b_hi = smem_u32(Wsm + L.w_off), b_lo = b_hi + (uint32_t)(Kpad * Npad * 4);
-        const uint32_t b_plane = (uint32_t)(Npad * 16);                   // one k-plane of W: Npad output rows x 16 bytes
+        // per k-step (8 of K): D[:, 0:2Npad] += A_hi * [W_hi | W_lo]  and  D[:, 0:Npad] += A_lo * W_hi   (the per-instruction
+        // cost of tcgen05.mma is ~64 cycles whatever N <= 128 is, so the hi*hi and hi*lo products share one instruction)
+        const uint32_t idesc2 = umma_idesc_tf32(2 * Npad), idesc1 = umma_idesc_tf32(Npad);
+        const uint32_t a_off = (uint32_t)((L.a_src == 0 ? x_plane0 : 0) * kPlaneBytes);
+        const uint32_t b_plane = (uint32_t)(2 * Npad * 16);               // one k-plane of W: 2 Npad rows x 16 bytes
+        uint64_t dah = umma_desc(smem_u32(stage_hi) + a_off, kPlaneBytes, 128);
+        uint64_t dal = umma_desc(smem_u32(stage_lo) + a_off, kPlaneBytes, 128);
+        uint64_t db = umma_desc(smem_u32(Wsm + L.w_off), b_plane, 128);
+        const uint64_t a_step = (uint64_t)((2 * kPlaneBytes) >> 4), b_step = (uint64_t)((2 * b_plane) >> 4);
         const int ksteps = Kpad >> 3;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const uint32_t ao = (uint32_t)(ks * 2 * kPlaneBytes), bo = (uint32_t)(ks * 2) * b_plane;
-          const uint64_t dah = umma_desc(a_hi + ao, kPlaneBytes, 128), dal = umma_desc(a_lo + ao, kPlaneBytes, 128);
-          const uint64_t dbh = umma_desc(b_hi + bo, b_plane, 128), dbl = umma_desc(b_lo + bo, b_plane, 128);
-          tc_mma_tf32(tmem_base, dal, dbh, idesc, ks > 0 ? 1u : 0u);      // small terms first
-          tc_mma_tf32(tmem_base, dah, dbl, idesc, 1u);
-          tc_mma_tf32(tmem_base, dah, dbh, idesc, 1u);
+        tc_mma_tf32(tmem_base, dah, db, idesc2, 0u);
+        tc_mma_tf32(tmem_base, dal, db, idesc1, 1u);
+        for (int ks = 1; ks < ksteps; ++ks) {
+          dah += a_step; dal += a_step; db += b_step;                     // start-address field only (no carry: < 256 KB)
+          tc_mma_tf32(tmem_base, dah, db, idesc2, 1u);
+          tc_mma_tf32(tmem_base, dal, db, idesc1, 1u);
         }
         tc_commit(&bar);
       }
+      if (tr) tr[3 + 4 * l] = clock64();
       mbar_wait(&bar, phase);
       phase ^= 1u;
       tc_fence_after();
-      // ---- epilogue: TMEM -> registers, bias, activation, then the consumer's layout
-      const int c_begin = half * (Npad >> 1), c_end = c_begin + (Npad >> 1);
+      if (tr) tr[4 + 4 * l] = clock64();
+      // ---- epilogue: TMEM -> registers (all loads in flight, one wait), bias, activation, then the consumer's layout
+      const int c_begin = half * (Npad >> 1);
+      const int nch = Npad >> 4;                              // 8-column chunks of this thread (Npad / 2 / 8) <= 5
       const float* bs = bias_s + L.bias_off;
-      for (int c0 = c_begin; c0 < c_end; c0 += 8) {
-        float v[8];
-        tc_ld8(t_lane + (uint32_t)c0, v);
-        if (dbg && l == dbg_layer && tile == 0) {          // debugging aid: raw accumulator of one layer, [128][Npad]
+      uint32_t acc[5][8], acc2[5][8];                          // hi*hi + lo*hi columns, hi*lo columns
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dbg[row * Npad + c0 + j] = v[j];
+      for (int j = 0; j < 5; ++j)
+        if (j < nch) {
+          tc_ld8_issue(t_lane + (uint32_t)(c_begin + 8 * j), acc[j]);
+          tc_ld8_issue(t_lane + (uint32_t)(Npad + c_begin + 8 * j), acc2[j]);
         }
+      tc_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          v[j] += bs[c0 + j];
-          if (L.relu) v[j] = fmaxf(v[j], 0.f);
-        }
-        const float4 x0 = make_float4(v[0], v[1], v[2], v[3]), x1 = make_float4(v[4], v[5], v[6], v[7]);
-        const int pl = c0 >> 2;
-        if (L.out_kind == 0) {
-          *reinterpret_cast<float4*>(hs + pl * kPlaneFloats + row * 4) = x0;
-          *reinterpret_cast<float4*>(hs + (pl + 1) * kPlaneFloats + row * 4) = x1;
-        } else if (L.out_kind == 1) {
-          float4 hi, lo;
-          split4(x0, hi, lo);
-          *reinterpret_cast<float4*>(stage_hi + pl * kPlaneFloats + row * 4) = hi;
-          *reinterpret_cast<float4*>(stage_lo + pl * kPlaneFloats + row * 4) = lo;
-          split4(x1, hi, lo);
-          *reinterpret_cast<float4*>(stage_hi + (pl + 1) * kPlaneFloats + row * 4) = hi;
-          *reinterpret_cast<float4*>(stage_lo + (pl + 1) * kPlaneFloats + row * 4) = lo;
-        } else if (row < R) {
-          float* qd = q_out + ((size_t)g0 * N + row) * CH;
+      for (int j = 0; j < 5; ++j) {
+        if (j < nch) {
+          const int c0 = c_begin + 8 * j;
+          float v[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (c0 + j < CH) qd[c0 + j] = v[j];
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[j][i]) + __uint_as_float(acc2[j][i]);
+          if (dbg && dbg_layer >= 0 && l == dbg_layer && tile == 0) {   // debugging aid: raw accumulator, [128][Npad]
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dbg[row * Npad + c0 + i] = v[i];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            v[i] += bs[c0 + i];
+            if (L.relu) v[i] = fmaxf(v[i], 0.f);
+          }
+          const float4 x0 = make_float4(v[0], v[1], v[2], v[3]), x1 = make_float4(v[4], v[5], v[6], v[7]);
+          const int pl = c0 >> 2;
+          if (L.out_kind == 2) {
+            if (row < R) {
+              float* qd = q_out + ((size_t)g0 * N + row) * CH;
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (c0 + i < CH) qd[c0 + i] = v[i];
+            }
+          } else {
+            if (L.out_kind == 0) {                           // combine stage: fp32 copy for the aggregation
+              *reinterpret_cast<float4*>(hs + pl * kPlaneFloats + row * 4) = x0;
+              *reinterpret_cast<float4*>(hs + (pl + 1) * kPlaneFloats + row * 4) = x1;
+            }
+            float4 hi, lo;
+            split4(x0, hi, lo);
+            *reinterpret_cast<float4*>(stage_hi + pl * kPlaneFloats + row * 4) = hi;
+            *reinterpret_cast<float4*>(stage_lo + pl * kPlaneFloats + row * 4) = lo;
+            split4(x1, hi, lo);
+            *reinterpret_cast<float4*>(stage_hi + (pl + 1) * kPlaneFloats + row * 4) = hi;
+            *reinterpret_cast<float4*>(stage_lo + (pl + 1) * kPlaneFloats + row * 4) = lo;
+          }
         }
       }
-      // ---- neighbour aggregation after a combine stage: as[pc][g, m] = sum_n Adj[g][n][m] * hs[pc][g, n]
+      // ---- neighbour aggregation after a combine stage: agg[pc][g, m] = sum_n Adj[g][n][m] * h[pc][g, n]  -> hi / lo planes
       if (L.out_kind == 0) {
         __syncthreads();
         const int items = FP * TG * MS;
         for (int item = tid; item < items; item += kTcThreads) {
-          const int pc = item % FP;
-          const int rest = item / FP;
-          const int g = rest % TG, ms = rest / TG;
+          const int ms = item % MS;                          // lanes of a warp share (plane, graph): broadcast reads
+          const int rest = item / MS;
+          const int g = rest % TG, pc = rest / TG;
           const int m0 = ms, m1 = ms + MS;
           const uint32_t k0 = mask_s[g * N + m0];
           const uint32_t k1 = (m1 < N) ? mask_s[g * N + m1] : 0u;
           const float* src = hs + pc * kPlaneFloats + (g * N) * 4;
           float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-          for (int n = 0; n < N; ++n) {
-            const float4 x = *reinterpret_cast<const float4*>(src + n * 4);
-            if (k0 & (1u << n)) { a0.x += x.x; a0.y += x.y; a0.z += x.z; a0.w += x.w; }
-            if (k1 & (1u << n)) { a1.x += x.x; a1.y += x.y; a1.z += x.z; a1.w += x.w; }
+          int n = 0;
+          for (; n + 4 <= N; n += 4) {
+            const float4 y0 = *reinterpret_cast<const float4*>(src + n * 4), y1 = *reinterpret_cast<const float4*>(src + n * 4 + 4);
+            const float4 y2 = *reinterpret_cast<const float4*>(src + n * 4 + 8), y3 = *reinterpret_cast<const float4*>(src + n * 4 + 12);
+            const uint32_t b0 = k0 >> n, b1 = k1 >> n;
+            if (b0 & 1u) padd4(a0, y0);
+            if (b1 & 1u) padd4(a1, y0);
+            if (b0 & 2u) padd4(a0, y1);
+            if (b1 & 2u) padd4(a1, y1);
+            if (b0 & 4u) padd4(a0, y2);
+            if (b1 & 4u) padd4(a1, y2);
+            if (b0 & 8u) padd4(a0, y3);
+            if (b1 & 8u) padd4(a1, y3);
           }
-          float* dst = as + pc * kPlaneFloats + (g * N) * 4;
-          *reinterpret_cast<float4*>(dst + m0 * 4) = a0;
-          if (m1 < N) *reinterpret_cast<float4*>(dst + m1 * 4) = a1;
+          for (; n < N; ++n) {
+            const float4 y = *reinterpret_cast<const float4*>(src + n * 4);
+            if (k0 & (1u << n)) padd4(a0, y);
+            if (k1 & (1u << n)) padd4(a1, y);
+          }
+          float4 hi, lo;
+          const int at = (FP + pc) * kPlaneFloats + (g * N) * 4;
+          split4(a0, hi, lo);
+          *reinterpret_cast<float4*>(stage_hi + at + m0 * 4) = hi;
+          *reinterpret_cast<float4*>(stage_lo + at + m0 * 4) = lo;
+          if (m1 < N) {
+            split4(a1, hi, lo);
+            *reinterpret_cast<float4*>(stage_hi + at + m1 * 4) = hi;
+            *reinterpret_cast<float4*>(stage_lo + at + m1 * 4) = lo;
+          }
         }
-        __syncthreads();                  // the next layer's split pass reads the aggregated planes
       }
+      if (tr) tr[5 + 4 * l] = clock64();
     }
     tc_fence_before();
     __syncthreads();                      // the tile's last TMEM reads and shared-memory reads are done
@@ -351,7 +433,8 @@ int tc_build_plan(const TcShape& s, TcPlan* out) {
   P.w_floats = w_floats;
   P.bias_floats = (bias_floats + 63) & ~63;
   P.stage_planes = stage_planes;
-  const size_t bytes = (size_t)(P.w_floats + P.bias_floats) * 4 + (size_t)(P.x_planes + 2 * (F / 4) + 2 * stage_planes) * kPlaneBytes +
+  V2V_REQUIRE(P.x_planes * kTcRows <= kTcMaxInItems * kTcThreads, "tensor-core forward: %d input planes unsupported", P.x_planes);
+  const size_t bytes = (size_t)(P.w_floats + P.bias_floats) * 4 + (size_t)(F / 4 + 2 * stage_planes) * kPlaneBytes +
                        (size_t)kTcRows * 4 + 64;
   V2V_REQUIRE(bytes <= 227 * 1024, "tensor-core forward: %zu bytes of shared memory do not fit", bytes);
   P.smem_bytes = (int)bytes;
