@@ -301,6 +301,11 @@ def run_engine_arm(a):
                       "adjacency bit-packed on the host), pipelined H2D, fwd+bwd+Adam, D2H of the per-head losses, one "
                       "stream synchronisation per call"}
 
+    # ---- predict (forward only) at the north-star batch: FP32-pipe fused kernel vs the tcgen05 3xTF32 kernel
+    predict = None
+    if rank == 0:
+        predict = predict_point(v2v, dev, a.agg_batch, N, S, a.sparse)
+
     # ---- roofline of the neighbour-aggregation kernel at the north-star point
     roof = None
     if rank == 0:
@@ -327,11 +332,48 @@ def run_engine_arm(a):
                              f"> 126 MiB L2); roofline loop rotates over buffer sets > L2 as well",
                        "final_loss": loss_now},
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roof, "cpu_baseline": cpu, "peaks": peaks,
+            "roofline": roof, "cpu_baseline": cpu, "peaks": peaks, "predict": predict,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def predict_point(v2v, dev, B, N, S, sparse):
+    """BS.predict on device-resident inputs (forward only), both kernels, CUDA events over 50 launches each."""
+    import torch
+    rng = np.random.default_rng(SEED + 7)
+    brain = v2v.BS(N, 3, 1, 16, 1, 4, stages=S, per_slot=False, max_batch=B, data_parallel=False, seed=SEED)
+    nb = min(B, 2048)
+    node, edge, adj = synth_numpy(nb, N, rng, sparse)
+    rep = -(-B // nb)
+    nd, ed, ad = (torch.from_numpy(np.tile(t, (rep, 1, 1))[:B]).to(dev) for t in (node, edge, adj))
+    im, _, _ = v2v.pack_adjacency(ad)
+    q = torch.empty((B, N, 4), device=dev)
+    out = {"batch": B, "unit": "us per forward of the whole batch"}
+    if not brain.tensor_core_info()["capable"]:
+        return None
+    ref = None
+    for name, mode in (("fp32_pipe_fused_us", 0), ("tcgen05_3xtf32_us", 2)):
+        brain.set_tensor_core(mode)
+        for _ in range(5):
+            brain.forward_device(nd, ed, in_mask=im, out=q)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            brain.forward_device(nd, ed, in_mask=im, out=q)
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = 1e3 * e0.elapsed_time(e1) / 50
+        if ref is None:
+            ref = q.clone()
+        else:
+            out["max_rel_diff_between_kernels"] = float((q - ref).abs().max() / ref.abs().max())
+    out["graphs_per_s_tcgen05"] = B / (out["tcgen05_3xtf32_us"] * 1e-6)
+    out["note"] = ("same inputs and weights; the tcgen05 kernel issues every contraction as tcgen05.mma kind::tf32 on hi/lo "
+                   "operand splits (fp32-grade products), accumulators in TMEM; automatic selection uses it from 4 tiles per SM")
+    return out
 
 
 def load_peaks():

@@ -99,7 +99,7 @@ struct v2v_brain {
   bool defer_reduce = false;
   // tensor-core (tcgen05) forward of the shared-weight brain
   bool tc_capable = false;
-  int tc_mode = 1;                              // 0: off, 1: auto (batches with >= 8 tiles per SM), 2: always
+  int tc_mode = 1;                              // 0: off, 1: auto (batches with >= 4 tiles per SM), 2: always
   TcPlan tc_plan;
   TcPlan* tc_plan_dev = nullptr;
 };
@@ -409,7 +409,7 @@ extern "C" int v2v_brain_forward(v2v_brain* b, const float* node_dev, const floa
   V2V_REQUIRE(node_dev && edge_dev && q_dev, "v2v_brain_forward: null pointer");
   V2V_REQUIRE(in_mask_dev || adj_dev, "v2v_brain_forward: need in_mask or adj");
   if (b->tc_capable && b->tc_mode > 0 && b->fused_enabled && in_mask_dev && !neighbor_dev &&
-      (b->tc_mode >= 2 || ceil_div(B, b->tc_plan.TG) >= 8 * sm_count()))
+      (b->tc_mode >= 2 || ceil_div(B, b->tc_plan.TG) >= 4 * sm_count()))
     return tc_forward_launch(b->tc_plan, b->tc_plan_dev, b->params[target ? 1 : 0], node_dev, edge_dev, in_mask_dev, q_dev, B,
                              (cudaStream_t)stream);
   if (use_fused(b, in_mask_dev, neighbor_dev)) {
@@ -660,7 +660,7 @@ static int stage_views(v2v_brain* b, const v2v_host_view* node, int n_node, cons
 
 extern "C" int v2v_host_stage_threads(void) { return host_stage_threads(); }
 
-// mode 0: never, 1: automatic (batches that give every SM at least eight 128-row tiles), 2: whenever the brain is capable
+// mode 0: never, 1: automatic (batches that give every SM at least four 128-row tiles), 2: whenever the brain is capable
 extern "C" int v2v_brain_set_tensor_core(v2v_brain* b, int mode) {
   V2V_REQUIRE(b, "v2v_brain_set_tensor_core: null brain");
   V2V_REQUIRE(mode >= 0 && mode <= 2, "v2v_brain_set_tensor_core: mode %d outside [0,2]", mode);

@@ -12,8 +12,8 @@
 //   * fp32 parity (1e-4, north star) rules out single-pass TF32 (10-bit mantissa), so every operand is split
 //     x = hi + lo into two TF32 values and every k-step issues THREE tcgen05.mma.kind::tf32 into the same fp32 TMEM
 //     accumulator: hi*hi + hi*lo + lo*hi (the dropped lo*lo term is 2^-22 relative);
-//   * one elected thread issues the MMAs and a tcgen05.commit on an mbarrier; all 8 warps then read the accumulator
-//     with tcgen05.ld (warp w: lanes 32*(w%4).., column half w/4; all loads in flight, one wait), add the bias, apply
+//   * one elected thread issues the MMAs and a tcgen05.commit on an mbarrier; all 16 warps then read the accumulator
+//     with tcgen05.ld (warp w: lanes 32*(w%4).., 8-column chunks dealt by w/4; all loads in flight, one wait), add the bias, apply
 //     ReLU and write the NEXT layer's operand planes already split into hi/lo -- there is no separate split pass:
 //     the tile loader, the combine epilogue and the aggregation all emit hi/lo planes directly, and the next tile's
 //     inputs are prefetched into registers while the current tile computes;
@@ -102,7 +102,7 @@ __device__ __forceinline__ void padd4(float4& a, const float4& v) {
   a.x = lo.x; a.y = lo.y; a.z = hi.x; a.w = hi.y;
 }
 
-constexpr int kTcMaxInItems = 2;       // x0 items (row, plane) per thread: x_planes * 128 / 256
+constexpr int kTcMaxInItems = 1;       // x0 items (row, plane) per thread: x_planes * 128 / 512
 
 // Shared-memory operand planes of a tile ("stage", hi and lo copies): [h (F/4) | aggregated (F/4) | x0 (x_planes)] for
 // the combine layers and the first MLP layer, then re-used as [previous layer's output] for the rest of the MLP.
@@ -153,10 +153,10 @@ tc_forward_kernel(const TcPlan* __restrict__ P, const float* __restrict__ params
   }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  const int q4 = warp & 3, half = warp >> 2;
+  const int q4 = warp & 3, cq = warp >> 2;                    // TMEM lane quarter, column quarter
   const int row = q4 * 32 + lane;                             // this thread's accumulator lane = tile row
   const int num_tiles = (B + TG - 1) / TG;
-  const int MS = (N + 1) >> 1;                                // aggregation: two targets per item
+  const int MS = N;                                           // aggregation: one target per item (F/4 * TG * N <= 512 items)
   const int x_plane0 = 2 * FP;                                // x0 lives behind h and agg in the operand planes
   uint32_t phase = 0;
 
@@ -246,26 +246,27 @@ tc_forward_kernel(const TcPlan* __restrict__ P, const float* __restrict__ params
         tc_commit(&bar);
       }
       if (tr) tr[3 + 4 * l] = clock64();
-      mbar_wait(&bar, phase);
+      mbar_wait(&bar, phase);             // (letting only the issuer poll and parking the rest in a CTA barrier measured no faster)
       phase ^= 1u;
       tc_fence_after();
       if (tr) tr[4 + 4 * l] = clock64();
       // ---- epilogue: TMEM -> registers (all loads in flight, one wait), bias, activation, then the consumer's layout
-      const int c_begin = half * (Npad >> 1);
-      const int nch = Npad >> 4;                              // 8-column chunks of this thread (Npad / 2 / 8) <= 5
+      // columns are dealt to the 4 column quarters in 8-column chunks: chunk j of this thread = 8 * (cq + 4 j)
+      const int nchunks = Npad >> 3;
+      const int nch = (nchunks - cq + 3) >> 2;               // <= 3 for Npad <= 96
       const float* bs = bias_s + L.bias_off;
-      uint32_t acc[5][8], acc2[5][8];                          // hi*hi + lo*hi columns, hi*lo columns
+      uint32_t acc[3][8], acc2[3][8];                          // hi*hi + lo*hi columns, hi*lo columns
 #pragma unroll
-      for (int j = 0; j < 5; ++j)
+      for (int j = 0; j < 3; ++j)
         if (j < nch) {
-          tc_ld8_issue(t_lane + (uint32_t)(c_begin + 8 * j), acc[j]);
-          tc_ld8_issue(t_lane + (uint32_t)(Npad + c_begin + 8 * j), acc2[j]);
+          tc_ld8_issue(t_lane + (uint32_t)(8 * (cq + 4 * j)), acc[j]);
+          tc_ld8_issue(t_lane + (uint32_t)(Npad + 8 * (cq + 4 * j)), acc2[j]);
         }
       tc_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 5; ++j) {
+      for (int j = 0; j < 3; ++j) {
         if (j < nch) {
-          const int c0 = c_begin + 8 * j;
+          const int c0 = 8 * (cq + 4 * j);
           float v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[j][i]) + __uint_as_float(acc2[j][i]);
@@ -378,7 +379,7 @@ int tc_build_plan(const TcShape& s, TcPlan* out) {
   int n = 0;
   auto finish = [&](TcLayer& L) {
     V2V_REQUIRE(L.Kpad % 8 == 0 && L.Kpad <= kTcMaxK, "tensor-core forward: contraction length %d unsupported", L.Kpad);
-    V2V_REQUIRE(L.Npad >= 16 && L.Npad <= 128, "tensor-core forward: layer width %d unsupported", L.Npad);
+    V2V_REQUIRE(L.Npad >= 16 && L.Npad <= 96, "tensor-core forward: layer width %d unsupported", L.Npad);
     L.w_off = w_floats; w_floats += 2 * L.Kpad * L.Npad;
     L.bias_off = bias_floats; bias_floats += L.Npad;
     stage_planes = std::max(stage_planes, L.Kpad / 4);

@@ -6,7 +6,7 @@ namespace v2v {
 
 constexpr int kTcMaxLayers = 12;       // up to 8 combine stages + the 4-layer decision MLP
 constexpr int kTcMaxK = 96;            // padded contraction length of one layer
-constexpr int kTcThreads = 256;
+constexpr int kTcThreads = 512;         // 16 warps: 4 lane quarters x 4 column quarters in the epilogues
 constexpr int kTcRows = 128;           // rows of a tile = TMEM lanes = UMMA M
 
 struct TcLayer {
