@@ -121,6 +121,32 @@ def test_agg_weighted_dense_path(v2v):
     assert rel_err(outT.cpu().numpy(), O.agg_factored_T(H.astype(np.float64), adj.astype(np.float64))) <= RTOL_F32
 
 
+@pytest.mark.parametrize("B,N,kind", [
+    (300, 33, "random"),      # warp-per-tile walk, W = 2, mask span not 16-byte aligned
+    (2000, 64, "dense"),      # warp-per-tile walk, one graph per tile, clear-bit walk
+    (777, 48, "sparse2"),     # set-bit walk
+    (1500, 100, "dense"),     # CTA-per-graph ring, W = 4, several graphs per CTA
+    (2600, 128, "random"),    # more graphs than resident CTAs: both ring stages refill
+    (310, 256, "sparse2"), (40, 200, "full"), (9, 97, "empty"), (130, 129, "random"),   # W = 5: unaligned mask rows
+])
+def test_agg_mask_large_graphs(v2v, B, N, kind):
+    """20 < N <= 256: the bit-walk kernels (csrc/agg_kernels.cuh), forward and transposed + addend, fp32 and bf16."""
+    rng = np.random.default_rng(B + 7 * N)
+    adj = rand_adj(rng, B, N, kind)
+    H = rng.normal(size=(B, N, 16)).astype(np.float32)
+    im, om, _ = v2v.pack_adjacency(dev(adj))
+    ref = O.agg_factored(H.astype(np.float64), adj)
+    out = v2v.aggregate(dev(H), mask=im)
+    assert rel_err(out.cpu().numpy(), ref) <= RTOL_F32
+    add = rng.normal(size=(B, N, 16)).astype(np.float32)
+    outT = v2v.aggregate(dev(H), mask=om, addend=dev(add))
+    assert rel_err(outT.cpu().numpy(), O.agg_factored_T(H.astype(np.float64), adj) + add) <= RTOL_F32
+    Hb = dev(H).to(torch.bfloat16)
+    outb = v2v.aggregate(Hb, mask=im)
+    refb = O.agg_factored(Hb.float().cpu().numpy().astype(np.float64), adj)
+    assert rel_err(outb.float().cpu().numpy(), refb) <= 1e-2                    # bf16 rounding of the stored result
+
+
 def test_agg_properties_at_full_size(v2v):
     """BASELINE size (B=8192, N=20): linearity and the edge-count checksum, no oracle loop needed."""
     rng = np.random.default_rng(1001)
