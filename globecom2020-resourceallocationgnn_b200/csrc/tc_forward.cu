@@ -3,23 +3,23 @@
 // The combine layers (GNNLayer.call, :44-51) and the decision MLP (:176-200) are genuine dense contractions
 // [rows x K] x [K x O]; here they run on the 5th-generation tensor cores:
 //   * a tile = TG = floor(128 / N) whole graphs = up to 128 node rows = the 128 TMEM lanes of one accumulator (UMMA M = 128);
-//   * every operand lives in shared memory as 4-feature PLANES  plane[k / 4][row][k % 4]  (2 KB per plane): this is the
-//     no-swizzle K-major core-matrix layout of the A operand (8 rows x 16 bytes contiguous, SBO = 128 B, LBO = one plane),
-//     concatenations ([h | agg | node,edge], :154-175) are plane lists, and the weights W[k][o] are staged once per CTA
-//     in the same form with o as the row (plane[k / 4][o][k % 4] = K-major B operand, LBO = one plane).  (A probe
-//     of the descriptor conventions, scratch/tc_probe.cu, showed MN-major TF32 operands reading as zeros without
-//     swizzle, so both operands are K-major);
-//   * fp32 parity (1e-4, north star) rules out single-pass TF32 (10-bit mantissa), so every operand is split
-//     x = hi + lo into two TF32 values and every k-step issues THREE tcgen05.mma.kind::tf32 into the same fp32 TMEM
-//     accumulator: hi*hi + hi*lo + lo*hi (the dropped lo*lo term is 2^-22 relative);
-//   * one elected thread issues the MMAs and a tcgen05.commit on an mbarrier; all 16 warps then read the accumulator
-//     with tcgen05.ld (warp w: lanes 32*(w%4).., 8-column chunks dealt by w/4; all loads in flight, one wait), add the bias, apply
-//     ReLU and write the NEXT layer's operand planes already split into hi/lo -- there is no separate split pass:
-//     the tile loader, the combine epilogue and the aggregation all emit hi/lo planes directly, and the next tile's
-//     inputs are prefetched into registers while the current tile computes;
-//   * the neighbour aggregation between the combine stages is the same register gather-reduce over bit masks as in the
-//     FP32 kernel, on the plane layout (zero HBM traffic).
-// Used for predict at batch sizes that give every SM at least two tiles; smaller batches stay on the FP32-pipe fused
+//   * shared-memory operands are 4-feature PLANES  plane[k / 4][row][k % 4]  (2 KB per plane): the no-swizzle K-major
+//     core-matrix layout (8 rows x 16 bytes contiguous, SBO = 128 B, LBO = one plane), so the reference's concatenations
+//     ([h | agg | node,edge], :154-175) are plane lists; the weights W[k][o] are staged once per CTA in the same form with
+//     o as the row, hi and lo halves of a k-plane adjacent (plane[k / 4][o | Npad + o][k % 4]).  (MN-major TF32 operands
+//     without swizzle read as zeros -- scratch/tc_probe.cu -- so both operands are K-major);
+//   * fp32 parity (1e-4, north star) rules out single-pass TF32, so every operand is split x = hi + lo (hi = TF32
+//     truncation: one LOP; lo = x - hi: one FADD) and each k-step of 8 issues TWO tcgen05.mma.kind::tf32 into one fp32
+//     accumulator: A_hi * [W_hi | W_lo] (hi*hi and hi*lo share an instruction through N-concatenation) and A_lo * W_hi;
+//     the epilogue adds the two column halves.  The per-instruction cost (~75 cycles) does not depend on N here;
+//   * the decision MLP never leaves tensor memory: the epilogue of layer j writes relu(acc + bias), split, back over its
+//     own accumulator columns with tcgen05.st and layer j+1 takes its A operand from TMEM (TS form);
+//   * warp specialisation with TWO tiles in flight: warp 16 only issues MMAs (waits on an "operands ready" mbarrier per
+//     tile slot, commits to an "accumulator ready" mbarrier), the 16 epilogue warps alternate between the two slots
+//     (tcgen05.ld with all loads in flight and one wait, bias, ReLU, hi/lo, the in-shared-memory neighbour aggregation
+//     after a combine stage), so the tensor pipe works on one tile while the CUDA cores finish the other's epilogue;
+//     each slot owns 256 of the 512 TMEM columns and its own operand planes; the next tiles' inputs wait in registers.
+// Used for predict at batch sizes that give every SM several tiles; smaller batches stay on the FP32-pipe fused
 // kernel, which has finer tiles (see brain.cu).
 #include <algorithm>
 
@@ -31,7 +31,8 @@ namespace {
 
 constexpr int kPlaneBytes = kTcRows * 16;      // one plane: 128 rows x 4 floats
 constexpr int kPlaneFloats = kTcRows * 4;
-constexpr uint32_t kTmemCols = 256;            // accumulator columns (power of two >= 2 x the widest layer, 2 x 80)
+constexpr uint32_t kTmemCols = 512;            // two tile slots x 256 columns
+constexpr int kSlotCols = 256, kRegionY = 160;   // a slot: region X = columns [0, 160), region Y = [160, 256)
 
 // ---- tcgen05 primitives (inline PTX, sm_100a) ------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {          // one full warp
@@ -56,6 +57,26 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the A operand in tensor memory (lane = row, column = k): the MLP chain
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const float4& a, const float4& b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "f"(a.x), "f"(a.y),
+               "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiThreads) : "memory"); }
 // 8 consecutive accumulator columns of this thread's TMEM lane
 __device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8]) {
   uint32_t r[8];
@@ -102,38 +123,51 @@ __device__ __forceinline__ void padd4(float4& a, const float4& v) {
   a.x = lo.x; a.y = lo.y; a.z = hi.x; a.w = hi.y;
 }
 
-constexpr int kTcMaxInItems = 1;       // x0 items (row, plane) per thread: x_planes * 128 / 512
+struct TcSlot {                          // per tile slot: shared-memory operand planes, fp32 h planes, masks
+  float* hs;
+  float* stage_hi;
+  float* stage_lo;
+  uint32_t* mask_s;
+};
 
-// Shared-memory operand planes of a tile ("stage", hi and lo copies): [h (F/4) | aggregated (F/4) | x0 (x_planes)] for
-// the combine layers and the first MLP layer, then re-used as [previous layer's output] for the rest of the MLP.
-// Nothing is ever split in a separate pass: the tile loader writes x0 as hi/lo, the combine epilogue writes h as fp32
-// (for the aggregation) and as hi/lo, the aggregation writes its result as hi/lo.
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_forward_kernel(const TcPlan* __restrict__ P, const float* __restrict__ params, const float* __restrict__ node,
                   const float* __restrict__ edge, const uint32_t* __restrict__ in_mask, float* __restrict__ q_out, int B,
                   float* __restrict__ dbg, int dbg_layer) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t ops_bar[2];        // operands of the slot's next layer are in place (512 arrivals)
+  __shared__ __align__(8) uint64_t acc_bar[2];        // the slot's accumulator is complete (tcgen05.commit)
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = P->N, TG = P->TG, Dn = P->Dn, De = P->De, CH = P->CH, XP = P->x_planes, dn_pad = P->dn_pad;
   const int FP = P->F >> 2;                                   // planes of h / agg
   const int n_layers = P->n_layers;
-  const int SP = P->stage_planes;
+  const int SP = P->stage_planes;                             // shared-memory operand planes per slot
 
   float* Wsm = reinterpret_cast<float*>(smem);
   float* bias_s = Wsm + P->w_floats;
-  float* hs = bias_s + P->bias_floats;                        // h planes (fp32, read by the aggregation)
-  float* stage_hi = hs + FP * kPlaneFloats;                   // MMA operand planes, hi / lo
-  float* stage_lo = stage_hi + SP * kPlaneFloats;
-  uint32_t* mask_s = reinterpret_cast<uint32_t*>(stage_lo + SP * kPlaneFloats);
-
+  TcSlot slot[2];
+  {
+    float* p = bias_s + P->bias_floats;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      slot[s].hs = p; p += FP * kPlaneFloats;
+      slot[s].stage_hi = p; p += SP * kPlaneFloats;
+      slot[s].stage_lo = p; p += SP * kPlaneFloats;
+      slot[s].mask_s = reinterpret_cast<uint32_t*>(p); p += kTcRows;
+    }
+  }
   if (tid == 0) {
-    mbar_init(&bar, 1);
+    mbar_init(&ops_bar[0], kTcEpiThreads); mbar_init(&ops_bar[1], kTcEpiThreads);
+    mbar_init(&acc_bar[0], 1); mbar_init(&acc_bar[1], 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, kTmemCols);
-  for (int i = tid; i < 2 * SP * kPlaneFloats; i += kTcThreads) stage_hi[i] = 0.f;   // finite everywhere (padding rows)
+  {                                                           // operand planes finite everywhere (padding rows)
+    float* z = slot[0].hs;
+    const int nz = 2 * ((FP + 2 * SP) * kPlaneFloats + kTcRows);
+    for (int i = tid; i < nz; i += kTcThreads) z[i] = 0.f;
+  }
   asm volatile("griddepcontrol.wait;" ::: "memory");          // parameters may come from the preceding optimiser kernel
   // ---- weights: parameters -> hi/lo planes over k (K-major B operand), biases zero-padded
   for (int l = 0; l < n_layers; ++l) {
@@ -152,205 +186,214 @@ tc_forward_kernel(const TcPlan* __restrict__ P, const float* __restrict__ params
     for (int o = tid; o < Npad; o += kTcThreads) bias_s[L.bias_off + o] = (o < No) ? params[L.pb_off + o] : 0.f;
   }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-
-  const int q4 = warp & 3, cq = warp >> 2;                    // TMEM lane quarter, column quarter
-  const int row = q4 * 32 + lane;                             // this thread's accumulator lane = tile row
-  const int num_tiles = (B + TG - 1) / TG;
-  const int MS = N;                                           // aggregation: one target per item (F/4 * TG * N <= 512 items)
-  const int x_plane0 = 2 * FP;                                // x0 lives behind h and agg in the operand planes
-  uint32_t phase = 0;
-
-  // ---- input prefetch: the next tile's node / edge features and mask words wait in registers
-  float xin[kTcMaxInItems][4];
-  uint32_t min_ = 0u;
-  auto fetch = [&](int tile) {
-    const int g0 = tile * TG;
-    const int R = (tile < num_tiles) ? min(TG, B - g0) * N : 0;
-#pragma unroll
-    for (int it = 0; it < kTcMaxInItems; ++it) {
-      const int idx = tid + it * kTcThreads;
-      const int r = idx & (kTcRows - 1), pl = idx >> 7;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) xin[it][j] = 0.f;
-      if (pl < XP && r < R) {
-        const size_t gr = (size_t)g0 * N + r;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int f = pl * 4 + j;
-          if (f < Dn) xin[it][j] = __ldg(node + gr * Dn + f);
-          else if (f >= dn_pad && f - dn_pad < De) xin[it][j] = __ldg(edge + gr * De + (f - dn_pad));
-        }
-      }
-    }
-    min_ = (tid < TG * N && tid < R) ? __ldg(in_mask + (size_t)g0 * N + tid) : 0u;
-  };
-  fetch(blockIdx.x);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16);
+  const int num_tiles = (B + TG - 1) / TG;
+  const int G = gridDim.x;
+  const int x_plane0 = 2 * FP;                                // x0 lives behind h and agg in the operand planes
 
-  // profiling aid (dbg_layer == -2): thread 0 of CTA 0 stamps clock64() at the phase boundaries of its second tile
-  long long* trace = (dbg && dbg_layer == -2 && blockIdx.x == 0 && tid == 0) ? reinterpret_cast<long long*>(dbg) : nullptr;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    long long* tr = (trace && tile == blockIdx.x + gridDim.x) ? trace : nullptr;
-    if (tr) tr[0] = clock64();
-    const int g0 = tile * TG;
-    const int ng = min(TG, B - g0);
-    const int R = ng * N;
-    // ---- prefetched inputs -> x0 operand planes (hi / lo), masks; then start fetching the next tile
+  if (warp == kTcEpiThreads / 32) {
+    // =============================== MMA warp: one thread issues everything ===============================
+    if (lane == 0) {
+      uint32_t po[2] = {0u, 0u};
+      for (int tA = blockIdx.x; tA < num_tiles; tA += 2 * G) {
+        const bool validB = tA + G < num_tiles;
+        for (int l = 0; l < n_layers; ++l) {
+          const TcLayer& L = P->layers[l];
+          const int Kpad = L.Kpad, Npad = L.Npad;
+          const uint32_t idesc2 = umma_idesc_tf32(2 * Npad), idesc1 = umma_idesc_tf32(Npad);
+          const uint32_t b_plane = (uint32_t)(2 * Npad * 16);             // one k-plane of W: 2 Npad rows x 16 bytes
+          const uint64_t db0 = umma_desc(smem_u32(Wsm + L.w_off), b_plane, 128);
+          const uint64_t b_step = (uint64_t)((2 * b_plane) >> 4);
+          const int ksteps = Kpad >> 3;
 #pragma unroll
-    for (int it = 0; it < kTcMaxInItems; ++it) {
-      const int idx = tid + it * kTcThreads;
-      const int r = idx & (kTcRows - 1), pl = idx >> 7;
+          for (int s = 0; s < 2; ++s) {
+            if (s == 1 && !validB) break;
+            mbar_wait(&ops_bar[s], po[s]);
+            po[s] ^= 1u;
+            tc_fence_after();
+            const uint32_t tslot = tmem_base + (uint32_t)(s * kSlotCols);
+            const uint32_t d_t = tslot + (uint32_t)L.dcol;
+            uint64_t db = db0;
+            // per k-step (8 of K): D[:, 0:2Npad] += A_hi * [W_hi | W_lo]  and  D[:, 0:Npad] += A_lo * W_hi
+            if (L.a_src == 2) {                               // operand in tensor memory (written by the previous epilogue)
+              uint32_t ah = tslot + (uint32_t)L.acol, al = ah + (uint32_t)Kpad;
+              for (int ks = 0; ks < ksteps; ++ks, ah += 8u, al += 8u, db += b_step) {
+                tc_mma_tf32_ts(d_t, ah, db, idesc2, ks > 0 ? 1u : 0u);
+                tc_mma_tf32_ts(d_t, al, db, idesc1, 1u);
+              }
+            } else {
+              const uint32_t a_off = (uint32_t)((L.a_src == 0 ? x_plane0 : 0) * kPlaneBytes);
+              uint64_t dah = umma_desc(smem_u32(slot[s].stage_hi) + a_off, kPlaneBytes, 128);
+              uint64_t dal = umma_desc(smem_u32(slot[s].stage_lo) + a_off, kPlaneBytes, 128);
+              const uint64_t a_step = (uint64_t)((2 * kPlaneBytes) >> 4);
+              for (int ks = 0; ks < ksteps; ++ks, dah += a_step, dal += a_step, db += b_step) {
+                tc_mma_tf32(d_t, dah, db, idesc2, ks > 0 ? 1u : 0u);
+                tc_mma_tf32(d_t, dal, db, idesc1, 1u);
+              }
+            }
+            tc_commit(&acc_bar[s]);
+          }
+        }
+      }
+    }
+  } else {
+    // =============================== 16 epilogue warps ===============================
+    const int q4 = warp & 3, cq = warp >> 2;                  // TMEM lane quarter, column quarter
+    const int row = q4 * 32 + lane;                           // this thread's accumulator lane = tile row
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    const int MS = N;                                         // aggregation: one target per item (F/4 * TG * N <= 512)
+    uint32_t pa[2] = {0u, 0u};
+    // ---- input prefetch: each slot's next tile (node / edge features, mask word) waits in registers
+    float xin[2][4];
+    uint32_t min_[2] = {0u, 0u};
+    auto fetch = [&](int s, int tile) {
+      const int g0 = tile * TG;
+      const int R = (tile < num_tiles) ? min(TG, B - g0) * N : 0;
+      const int r = tid & (kTcRows - 1), pl = tid >> 7;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xin[s][j] = 0.f;
+      if (pl < XP && r < R) {
+        const size_t gr = (size_t)g0 * N + r;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int f = pl * 4 + j;
+          if (f < Dn) xin[s][j] = __ldg(node + gr * Dn + f);
+          else if (f >= dn_pad && f - dn_pad < De) xin[s][j] = __ldg(edge + gr * De + (f - dn_pad));
+        }
+      }
+      min_[s] = (tid < TG * N && tid < R) ? __ldg(in_mask + (size_t)g0 * N + tid) : 0u;
+    };
+    // prefetched inputs -> the slot's x0 operand planes (hi / lo) and masks; signals layer 0; fetches the slot's next tile
+    auto start_tile = [&](int s, int next_tile) {
+      const int r = tid & (kTcRows - 1), pl = tid >> 7;
       if (pl < XP) {
         float4 hi, lo;
-        split4(make_float4(xin[it][0], xin[it][1], xin[it][2], xin[it][3]), hi, lo);
-        *reinterpret_cast<float4*>(stage_hi + (x_plane0 + pl) * kPlaneFloats + r * 4) = hi;
-        *reinterpret_cast<float4*>(stage_lo + (x_plane0 + pl) * kPlaneFloats + r * 4) = lo;
+        split4(make_float4(xin[s][0], xin[s][1], xin[s][2], xin[s][3]), hi, lo);
+        *reinterpret_cast<float4*>(slot[s].stage_hi + (x_plane0 + pl) * kPlaneFloats + r * 4) = hi;
+        *reinterpret_cast<float4*>(slot[s].stage_lo + (x_plane0 + pl) * kPlaneFloats + r * 4) = lo;
+      }
+      if (tid < TG * N) slot[s].mask_s[tid] = min_[s];
+      fence_async_smem();
+      mbar_arrive(&ops_bar[s]);
+      fetch(s, next_tile);
+    };
+    fetch(0, blockIdx.x);
+    fetch(1, blockIdx.x + G);
+    for (int tA = blockIdx.x; tA < num_tiles; tA += 2 * G) {
+      const bool validB = tA + G < num_tiles;
+      start_tile(0, tA + 2 * G);
+      if (validB) start_tile(1, tA + 3 * G);
+      for (int l = 0; l < n_layers; ++l) {
+        const TcLayer& L = P->layers[l];
+        const int Npad = L.Npad;
+        const float* bs = bias_s + L.bias_off;
+        // columns are dealt to the 4 column quarters in 8-column chunks: chunk j of this thread = 8 * (cq + 4 j)
+        const int nch = ((Npad >> 3) - cq + 3) >> 2;          // <= 3 for Npad <= 96
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (s == 1 && !validB) break;
+          const int tile = tA + s * G;
+          const int g0 = tile * TG;
+          const int R = min(TG, B - g0) * N;
+          const TcSlot& S = slot[s];
+          const uint32_t t_d = t_lane + (uint32_t)(s * kSlotCols + L.dcol);
+          mbar_wait(&acc_bar[s], pa[s]);
+          pa[s] ^= 1u;
+          tc_fence_after();
+          // ---- TMEM -> registers (all loads in flight, one wait), bias, activation, then the consumer's layout
+          uint32_t acc[3][8], acc2[3][8];                    // hi*hi + lo*hi columns, hi*lo columns
+#pragma unroll
+          for (int j = 0; j < 3; ++j)
+            if (j < nch) {
+              tc_ld8_issue(t_d + (uint32_t)(8 * (cq + 4 * j)), acc[j]);
+              tc_ld8_issue(t_d + (uint32_t)(Npad + 8 * (cq + 4 * j)), acc2[j]);
+            }
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            if (j < nch) {
+              const int c0 = 8 * (cq + 4 * j);
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[j][i]) + __uint_as_float(acc2[j][i]);
+              if (dbg && dbg_layer >= 0 && l == dbg_layer && tile == 0) {   // debugging aid: raw accumulator, [128][Npad]
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dbg[row * Npad + c0 + i] = v[i];
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                v[i] += bs[c0 + i];
+                if (L.relu) v[i] = fmaxf(v[i], 0.f);
+              }
+              const float4 x0 = make_float4(v[0], v[1], v[2], v[3]), x1 = make_float4(v[4], v[5], v[6], v[7]);
+              if (L.out_kind == 2) {
+                if (row < R) {
+                  float* qd = q_out + ((size_t)g0 * N + row) * CH;
+#pragma unroll
+                  for (int i = 0; i < 8; ++i)
+                    if (c0 + i < CH) qd[c0 + i] = v[i];
+                }
+              } else {
+                float4 h0, l0, h1, l1;
+                split4(x0, h0, l0);
+                split4(x1, h1, l1);
+                if (L.out_kind == 1) {                       // MLP chain: back into tensor memory, over the accumulator
+                  tc_st8(t_d + (uint32_t)c0, h0, h1);
+                  tc_st8(t_d + (uint32_t)(Npad + c0), l0, l1);
+                } else {                                     // combine stage: fp32 copy for the aggregation + operand planes
+                  const int pl = c0 >> 2;
+                  *reinterpret_cast<float4*>(S.hs + pl * kPlaneFloats + row * 4) = x0;
+                  *reinterpret_cast<float4*>(S.hs + (pl + 1) * kPlaneFloats + row * 4) = x1;
+                  *reinterpret_cast<float4*>(S.stage_hi + pl * kPlaneFloats + row * 4) = h0;
+                  *reinterpret_cast<float4*>(S.stage_lo + pl * kPlaneFloats + row * 4) = l0;
+                  *reinterpret_cast<float4*>(S.stage_hi + (pl + 1) * kPlaneFloats + row * 4) = h1;
+                  *reinterpret_cast<float4*>(S.stage_lo + (pl + 1) * kPlaneFloats + row * 4) = l1;
+                }
+              }
+            }
+          }
+          // ---- neighbour aggregation after a combine stage: agg[pc][g, m] = sum_n Adj[g][n][m] * h[pc][g, n]  -> hi / lo planes
+          if (L.out_kind == 0) {
+            epi_barrier();
+            const int items = FP * TG * MS;
+            for (int item = tid; item < items; item += kTcEpiThreads) {
+              const int ms = item % MS;                      // lanes of a warp share (plane, graph): broadcast reads
+              const int rest = item / MS;
+              const int g = rest % TG, pc = rest / TG;
+              const uint32_t k0 = S.mask_s[g * N + ms];
+              const float* src = S.hs + pc * kPlaneFloats + (g * N) * 4;
+              float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f);
+              int n = 0;
+              for (; n + 4 <= N; n += 4) {
+                const float4 y0 = *reinterpret_cast<const float4*>(src + n * 4), y1 = *reinterpret_cast<const float4*>(src + n * 4 + 4);
+                const float4 y2 = *reinterpret_cast<const float4*>(src + n * 4 + 8), y3 = *reinterpret_cast<const float4*>(src + n * 4 + 12);
+                const uint32_t b0 = k0 >> n;
+                if (b0 & 1u) padd4(a0, y0);
+                if (b0 & 2u) padd4(a0, y1);
+                if (b0 & 4u) padd4(a0, y2);
+                if (b0 & 8u) padd4(a0, y3);
+              }
+              for (; n < N; ++n)
+                if (k0 & (1u << n)) padd4(a0, *reinterpret_cast<const float4*>(src + n * 4));
+              float4 hi, lo;
+              const int at = (FP + pc) * kPlaneFloats + (g * N + ms) * 4;
+              split4(a0, hi, lo);
+              *reinterpret_cast<float4*>(S.stage_hi + at) = hi;
+              *reinterpret_cast<float4*>(S.stage_lo + at) = lo;
+            }
+          }
+          if (L.out_kind != 2) {                              // hand the next layer's operands to the MMA warp
+            if (L.out_kind == 1) tc_wait_st(); else fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(&ops_bar[s]);
+          }
+        }
       }
     }
-    if (tid < TG * N) mask_s[tid] = min_;
-    fetch(tile + gridDim.x);
-    if (tr) tr[1] = clock64();
-
-    for (int l = 0; l < n_layers; ++l) {
-      const TcLayer& L = P->layers[l];
-      const int Kpad = L.Kpad, Npad = L.Npad;
-      fence_async_smem();                 // generic-proxy writes of the operand planes -> visible to the tensor core
-      tc_fence_before();                  // the previous epilogue's TMEM reads are ordered before the barrier
-      __syncthreads();
-      if (tr) tr[2 + 4 * l] = clock64();
-      // ---- one thread issues the 3xTF32 MMAs of the layer and commits them to the mbarrier
-      if (tid == 0) {
-        tc_fence_after();
-        // per k-step (8 of K): D[:, 0:2Npad] += A_hi * [W_hi | W_lo]  and  D[:, 0:Npad] += A_lo * W_hi   (the per-instruction
-        // cost of tcgen05.mma is ~64 cycles whatever N <= 128 is, so the hi*hi and hi*lo products share one instruction)
-        const uint32_t idesc2 = umma_idesc_tf32(2 * Npad), idesc1 = umma_idesc_tf32(Npad);
-        const uint32_t a_off = (uint32_t)((L.a_src == 0 ? x_plane0 : 0) * kPlaneBytes);
-        const uint32_t b_plane = (uint32_t)(2 * Npad * 16);               // one k-plane of W: 2 Npad rows x 16 bytes
-        uint64_t dah = umma_desc(smem_u32(stage_hi) + a_off, kPlaneBytes, 128);
-        uint64_t dal = umma_desc(smem_u32(stage_lo) + a_off, kPlaneBytes, 128);
-        uint64_t db = umma_desc(smem_u32(Wsm + L.w_off), b_plane, 128);
-        const uint64_t a_step = (uint64_t)((2 * kPlaneBytes) >> 4), b_step = (uint64_t)((2 * b_plane) >> 4);
-        const int ksteps = Kpad >> 3;
-        tc_mma_tf32(tmem_base, dah, db, idesc2, 0u);
-        tc_mma_tf32(tmem_base, dal, db, idesc1, 1u);
-        for (int ks = 1; ks < ksteps; ++ks) {
-          dah += a_step; dal += a_step; db += b_step;                     // start-address field only (no carry: < 256 KB)
-          tc_mma_tf32(tmem_base, dah, db, idesc2, 1u);
-          tc_mma_tf32(tmem_base, dal, db, idesc1, 1u);
-        }
-        tc_commit(&bar);
-      }
-      if (tr) tr[3 + 4 * l] = clock64();
-      mbar_wait(&bar, phase);             // (letting only the issuer poll and parking the rest in a CTA barrier measured no faster)
-      phase ^= 1u;
-      tc_fence_after();
-      if (tr) tr[4 + 4 * l] = clock64();
-      // ---- epilogue: TMEM -> registers (all loads in flight, one wait), bias, activation, then the consumer's layout
-      // columns are dealt to the 4 column quarters in 8-column chunks: chunk j of this thread = 8 * (cq + 4 j)
-      const int nchunks = Npad >> 3;
-      const int nch = (nchunks - cq + 3) >> 2;               // <= 3 for Npad <= 96
-      const float* bs = bias_s + L.bias_off;
-      uint32_t acc[3][8], acc2[3][8];                          // hi*hi + lo*hi columns, hi*lo columns
-#pragma unroll
-      for (int j = 0; j < 3; ++j)
-        if (j < nch) {
-          tc_ld8_issue(t_lane + (uint32_t)(8 * (cq + 4 * j)), acc[j]);
-          tc_ld8_issue(t_lane + (uint32_t)(Npad + 8 * (cq + 4 * j)), acc2[j]);
-        }
-      tc_wait_ld();
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        if (j < nch) {
-          const int c0 = 8 * (cq + 4 * j);
-          float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[j][i]) + __uint_as_float(acc2[j][i]);
-          if (dbg && dbg_layer >= 0 && l == dbg_layer && tile == 0) {   // debugging aid: raw accumulator, [128][Npad]
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dbg[row * Npad + c0 + i] = v[i];
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            v[i] += bs[c0 + i];
-            if (L.relu) v[i] = fmaxf(v[i], 0.f);
-          }
-          const float4 x0 = make_float4(v[0], v[1], v[2], v[3]), x1 = make_float4(v[4], v[5], v[6], v[7]);
-          const int pl = c0 >> 2;
-          if (L.out_kind == 2) {
-            if (row < R) {
-              float* qd = q_out + ((size_t)g0 * N + row) * CH;
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (c0 + i < CH) qd[c0 + i] = v[i];
-            }
-          } else {
-            if (L.out_kind == 0) {                           // combine stage: fp32 copy for the aggregation
-              *reinterpret_cast<float4*>(hs + pl * kPlaneFloats + row * 4) = x0;
-              *reinterpret_cast<float4*>(hs + (pl + 1) * kPlaneFloats + row * 4) = x1;
-            }
-            float4 hi, lo;
-            split4(x0, hi, lo);
-            *reinterpret_cast<float4*>(stage_hi + pl * kPlaneFloats + row * 4) = hi;
-            *reinterpret_cast<float4*>(stage_lo + pl * kPlaneFloats + row * 4) = lo;
-            split4(x1, hi, lo);
-            *reinterpret_cast<float4*>(stage_hi + (pl + 1) * kPlaneFloats + row * 4) = hi;
-            *reinterpret_cast<float4*>(stage_lo + (pl + 1) * kPlaneFloats + row * 4) = lo;
-          }
-        }
-      }
-      // ---- neighbour aggregation after a combine stage: agg[pc][g, m] = sum_n Adj[g][n][m] * h[pc][g, n]  -> hi / lo planes
-      if (L.out_kind == 0) {
-        __syncthreads();
-        const int items = FP * TG * MS;
-        for (int item = tid; item < items; item += kTcThreads) {
-          const int ms = item % MS;                          // lanes of a warp share (plane, graph): broadcast reads
-          const int rest = item / MS;
-          const int g = rest % TG, pc = rest / TG;
-          const int m0 = ms, m1 = ms + MS;
-          const uint32_t k0 = mask_s[g * N + m0];
-          const uint32_t k1 = (m1 < N) ? mask_s[g * N + m1] : 0u;
-          const float* src = hs + pc * kPlaneFloats + (g * N) * 4;
-          float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-          int n = 0;
-          for (; n + 4 <= N; n += 4) {
-            const float4 y0 = *reinterpret_cast<const float4*>(src + n * 4), y1 = *reinterpret_cast<const float4*>(src + n * 4 + 4);
-            const float4 y2 = *reinterpret_cast<const float4*>(src + n * 4 + 8), y3 = *reinterpret_cast<const float4*>(src + n * 4 + 12);
-            const uint32_t b0 = k0 >> n, b1 = k1 >> n;
-            if (b0 & 1u) padd4(a0, y0);
-            if (b1 & 1u) padd4(a1, y0);
-            if (b0 & 2u) padd4(a0, y1);
-            if (b1 & 2u) padd4(a1, y1);
-            if (b0 & 4u) padd4(a0, y2);
-            if (b1 & 4u) padd4(a1, y2);
-            if (b0 & 8u) padd4(a0, y3);
-            if (b1 & 8u) padd4(a1, y3);
-          }
-          for (; n < N; ++n) {
-            const float4 y = *reinterpret_cast<const float4*>(src + n * 4);
-            if (k0 & (1u << n)) padd4(a0, y);
-            if (k1 & (1u << n)) padd4(a1, y);
-          }
-          float4 hi, lo;
-          const int at = (FP + pc) * kPlaneFloats + (g * N) * 4;
-          split4(a0, hi, lo);
-          *reinterpret_cast<float4*>(stage_hi + at + m0 * 4) = hi;
-          *reinterpret_cast<float4*>(stage_lo + at + m0 * 4) = lo;
-          if (m1 < N) {
-            split4(a1, hi, lo);
-            *reinterpret_cast<float4*>(stage_hi + at + m1 * 4) = hi;
-            *reinterpret_cast<float4*>(stage_lo + at + m1 * 4) = lo;
-          }
-        }
-      }
-      if (tr) tr[5 + 4 * l] = clock64();
-    }
-    tc_fence_before();
-    __syncthreads();                      // the tile's last TMEM reads and shared-memory reads are done
   }
   tc_fence_before();
   __syncthreads();
@@ -377,12 +420,20 @@ int tc_build_plan(const TcShape& s, TcPlan* out) {
   auto r16 = [](int v) { return (v + 15) & ~15; };
   int w_floats = 0, bias_floats = 0, stage_planes = 0;
   int n = 0;
+  int prev_dcol = kRegionY;              // the first layer's accumulator goes to region X
   auto finish = [&](TcLayer& L) {
     V2V_REQUIRE(L.Kpad % 8 == 0 && L.Kpad <= kTcMaxK, "tensor-core forward: contraction length %d unsupported", L.Kpad);
     V2V_REQUIRE(L.Npad >= 16 && L.Npad <= 96, "tensor-core forward: layer width %d unsupported", L.Npad);
     L.w_off = w_floats; w_floats += 2 * L.Kpad * L.Npad;
     L.bias_off = bias_floats; bias_floats += L.Npad;
-    stage_planes = std::max(stage_planes, L.Kpad / 4);
+    if (L.a_src != 2) stage_planes = std::max(stage_planes, L.Kpad / 4);
+    // accumulators alternate between the slot's two TMEM regions; a chain layer reads its operand where the previous
+    // layer's epilogue left it (over that layer's accumulator)
+    L.acol = prev_dcol;
+    L.dcol = (L.a_src == 2) ? (prev_dcol == 0 ? kRegionY : 0) : 0;
+    const int room = L.dcol == 0 ? kRegionY : kSlotCols - kRegionY;
+    V2V_REQUIRE(2 * L.Npad <= room, "tensor-core forward: layer width %d does not fit its tensor-memory region", L.Npad);
+    prev_dcol = L.dcol;
     return 0;
   };
   // x0 plane features: node f (f < Dn), zero padding, edge e at dn_pad + e
@@ -434,9 +485,10 @@ int tc_build_plan(const TcShape& s, TcPlan* out) {
   P.w_floats = w_floats;
   P.bias_floats = (bias_floats + 63) & ~63;
   P.stage_planes = stage_planes;
-  V2V_REQUIRE(P.x_planes * kTcRows <= kTcMaxInItems * kTcThreads, "tensor-core forward: %d input planes unsupported", P.x_planes);
-  const size_t bytes = (size_t)(P.w_floats + P.bias_floats) * 4 + (size_t)(F / 4 + 2 * stage_planes) * kPlaneBytes +
-                       (size_t)kTcRows * 4 + 64;
+  V2V_REQUIRE(P.x_planes * kTcRows <= kTcEpiThreads, "tensor-core forward: %d input planes unsupported", P.x_planes);
+  V2V_REQUIRE((F / 4) * P.TG * s.N <= 4 * kTcEpiThreads, "tensor-core forward: aggregation items");
+  const size_t bytes = (size_t)(P.w_floats + P.bias_floats) * 4 +
+                       2 * ((size_t)(F / 4 + 2 * stage_planes) * kPlaneBytes + (size_t)kTcRows * 4) + 64;
   V2V_REQUIRE(bytes <= 227 * 1024, "tensor-core forward: %zu bytes of shared memory do not fit", bytes);
   P.smem_bytes = (int)bytes;
   return 0;

@@ -6,7 +6,8 @@ namespace v2v {
 
 constexpr int kTcMaxLayers = 12;       // up to 8 combine stages + the 4-layer decision MLP
 constexpr int kTcMaxK = 96;            // padded contraction length of one layer
-constexpr int kTcThreads = 512;         // 16 warps: 4 lane quarters x 4 column quarters in the epilogues
+constexpr int kTcEpiThreads = 512;      // 16 epilogue warps: 4 TMEM lane quarters x 4 column quarters
+constexpr int kTcThreads = kTcEpiThreads + 32;   // + one MMA-issuing warp
 constexpr int kTcRows = 128;           // rows of a tile = TMEM lanes = UMMA M
 
 struct TcLayer {
@@ -17,7 +18,9 @@ struct TcLayer {
   int w_off;             // shared-memory float offset of the layer's hi planes (lo planes follow at + Kpad * Npad)
   int bias_off;          // shared-memory float offset of the zero-padded bias
   int a_src;             // 0: x0 planes, 1: [h | agg | x0] planes (split on the fly), 2: the previous layer's epilogue output
-  int out_kind;          // 0: h planes (fp32), 1: next layer's operand (hi/lo planes), 2: Q to global memory
+  int out_kind;          // 0: h planes (fp32 + hi/lo) then aggregation, 1: next layer's operand (hi/lo, in TMEM), 2: Q to global
+  int dcol;              // accumulator base column inside the tile slot's 256 TMEM columns
+  int acol;              // a_src == 2: base column of the operand's hi half (lo half at acol + Kpad)
   short kmap[kTcMaxK];   // contraction index -> row of W in the parameter buffer (-1: zero row)
 };
 
