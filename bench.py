@@ -372,7 +372,7 @@ def predict_point(v2v, dev, B, N, S, sparse):
             out["max_rel_diff_between_kernels"] = float((q - ref).abs().max() / ref.abs().max())
     out["graphs_per_s_tcgen05"] = B / (out["tcgen05_3xtf32_us"] * 1e-6)
     out["note"] = ("same inputs and weights; the tcgen05 kernel issues every contraction as tcgen05.mma kind::tf32 on hi/lo "
-                   "operand splits (fp32-grade products), accumulators in TMEM; automatic selection uses it from 4 tiles per SM")
+                   "operand splits (fp32-grade products), accumulators in TMEM; one MMA warp + 16 epilogue warps, two tiles in flight per SM; automatic selection uses it from 2 tiles per SM")
     return out
 
 

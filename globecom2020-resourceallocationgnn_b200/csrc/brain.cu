@@ -99,9 +99,10 @@ struct v2v_brain {
   bool defer_reduce = false;
   // tensor-core (tcgen05) forward of the shared-weight brain
   bool tc_capable = false;
-  int tc_mode = 1;                              // 0: off, 1: auto (batches with >= 4 tiles per SM), 2: always
+  int tc_mode = 1;                              // 0: off, 1: auto (batches with >= 2 tiles per SM), 2: always
   TcPlan tc_plan;
   TcPlan* tc_plan_dev = nullptr;
+  float* tc_wimg = nullptr;                     // staged weight image (hi/lo planes + biases) of the last call
 };
 
 static FusedShape fused_shape(const v2v_brain* b) {
@@ -171,6 +172,7 @@ extern "C" void v2v_brain_destroy(v2v_brain* b) {
   if (b->pin) cudaFreeHost(b->pin);
   cudaFree(b->partial);
   cudaFree(b->tc_plan_dev);
+  cudaFree(b->tc_wimg);
   for (auto& kv : b->fused_cache) { cudaFree(kv.second->dev); delete kv.second; }
   delete b;
 }
@@ -255,7 +257,8 @@ extern "C" int v2v_brain_create(const v2v_brain_config* cfg, v2v_brain** out) {
     ts.H1 = cfg->hidden[0]; ts.H2 = cfg->hidden[1]; ts.H3 = cfg->hidden[2];
     ts.w_off = b->lw.data(); ts.b_off = b->lb.data();
     if (tc_build_plan(ts, &b->tc_plan) == 0 && cudaMalloc((void**)&b->tc_plan_dev, sizeof(TcPlan)) == cudaSuccess &&
-        cudaMemcpy(b->tc_plan_dev, &b->tc_plan, sizeof(TcPlan), cudaMemcpyHostToDevice) == cudaSuccess) {
+        cudaMemcpy(b->tc_plan_dev, &b->tc_plan, sizeof(TcPlan), cudaMemcpyHostToDevice) == cudaSuccess &&
+        cudaMalloc((void**)&b->tc_wimg, (size_t)(b->tc_plan.w_floats + b->tc_plan.bias_floats) * sizeof(float)) == cudaSuccess) {
       b->tc_capable = true;
     }
     last_error().clear();
@@ -409,9 +412,9 @@ extern "C" int v2v_brain_forward(v2v_brain* b, const float* node_dev, const floa
   V2V_REQUIRE(node_dev && edge_dev && q_dev, "v2v_brain_forward: null pointer");
   V2V_REQUIRE(in_mask_dev || adj_dev, "v2v_brain_forward: need in_mask or adj");
   if (b->tc_capable && b->tc_mode > 0 && b->fused_enabled && in_mask_dev && !neighbor_dev &&
-      (b->tc_mode >= 2 || ceil_div(B, b->tc_plan.TG) >= 4 * sm_count()))
-    return tc_forward_launch(b->tc_plan, b->tc_plan_dev, b->params[target ? 1 : 0], node_dev, edge_dev, in_mask_dev, q_dev, B,
-                             (cudaStream_t)stream);
+      (b->tc_mode >= 2 || ceil_div(B, b->tc_plan.TG) >= 2 * sm_count()))
+    return tc_forward_launch(b->tc_plan, b->tc_plan_dev, b->params[target ? 1 : 0], b->tc_wimg, node_dev, edge_dev, in_mask_dev,
+                             q_dev, B, (cudaStream_t)stream);
   if (use_fused(b, in_mask_dev, neighbor_dev)) {
     v2v_brain::FusedEntry* e = nullptr;
     if (int rc = fused_get(b, B, 0, &e)) return rc;
@@ -660,7 +663,7 @@ static int stage_views(v2v_brain* b, const v2v_host_view* node, int n_node, cons
 
 extern "C" int v2v_host_stage_threads(void) { return host_stage_threads(); }
 
-// mode 0: never, 1: automatic (batches that give every SM at least four 128-row tiles), 2: whenever the brain is capable
+// mode 0: never, 1: automatic (batches that give every SM at least two 128-row tiles (one per tile slot)), 2: whenever the brain is capable
 extern "C" int v2v_brain_set_tensor_core(v2v_brain* b, int mode) {
   V2V_REQUIRE(b, "v2v_brain_set_tensor_core: null brain");
   V2V_REQUIRE(mode >= 0 && mode <= 2, "v2v_brain_set_tensor_core: mode %d outside [0,2]", mode);
@@ -673,9 +676,9 @@ extern "C" int v2v_brain_set_tensor_core(v2v_brain* b, int mode) {
 extern "C" int v2v_brain_tc_debug(v2v_brain* b, const float* node, const float* edge, const uint32_t* in_mask, int B,
                                   int layer, float* q_dev, float* dbg_dev, int* npad_out, void* stream) {
   V2V_REQUIRE(b && b->tc_capable && layer >= -2 && layer < b->tc_plan.n_layers, "v2v_brain_tc_debug: bad arguments");
-  if (npad_out) *npad_out = layer >= 0 ? b->tc_plan.layers[layer].Npad : b->tc_plan.n_layers;   // -2: phase trace (clock64 stamps)
-  return tc_forward_launch(b->tc_plan, b->tc_plan_dev, b->params[0], node, edge, in_mask, q_dev, B, (cudaStream_t)stream,
-                           dbg_dev, layer);
+  if (npad_out) *npad_out = layer >= 0 ? b->tc_plan.layers[layer].Npad : b->tc_plan.n_layers;
+  return tc_forward_launch(b->tc_plan, b->tc_plan_dev, b->params[0], b->tc_wimg, node, edge, in_mask, q_dev, B,
+                           (cudaStream_t)stream, dbg_dev, layer);
 }
 extern "C" int v2v_brain_tensor_core_info(const v2v_brain* b, int* info4) {
   V2V_REQUIRE(b && info4, "v2v_brain_tensor_core_info: null argument");

@@ -123,6 +123,32 @@ __device__ __forceinline__ void padd4(float4& a, const float4& v) {
   a.x = lo.x; a.y = lo.y; a.z = hi.x; a.w = hi.y;
 }
 
+// Builds the shared-memory image of all weights (hi/lo k-planes, see below) and zero-padded biases ONCE per call in
+// global memory; every CTA of the forward kernel then pulls it with one bulk-async copy instead of re-deriving it.
+__global__ void __launch_bounds__(256)
+tc_stage_weights_kernel(const TcPlan* __restrict__ P, const float* __restrict__ params, float* __restrict__ wimg) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");          // parameters may come from the preceding optimiser kernel
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int n_layers = P->n_layers;
+  float* bias_img = wimg + P->w_floats;
+  for (int l = 0; l < n_layers; ++l) {
+    const TcLayer& L = P->layers[l];
+    const int Kpad = L.Kpad, Npad = L.Npad, No = L.N;
+    float* Wc = wimg + L.w_off;         // k-plane kc: rows [0, Npad) = hi(W[k][o]), rows [Npad, 2 Npad) = lo, 4 k's per row
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < Kpad * Npad; idx += gridDim.x * blockDim.x) {
+      const int o = idx % Npad, k = idx / Npad;               // consecutive threads read consecutive o of one W row
+      const int wrow = L.kmap[k];
+      const float w = (wrow >= 0 && o < No) ? params[L.pw_off + wrow * No + o] : 0.f;
+      const float h = tf32_rn(w);
+      const int at = (k >> 2) * (2 * Npad * 4) + o * 4 + (k & 3);
+      Wc[at] = h;
+      Wc[at + Npad * 4] = tf32_rn(w - h);
+    }
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < Npad; o += gridDim.x * blockDim.x)
+      bias_img[L.bias_off + o] = (o < No) ? params[L.pb_off + o] : 0.f;
+  }
+}
+
 struct TcSlot {                          // per tile slot: shared-memory operand planes, fp32 h planes, masks
   float* hs;
   float* stage_hi;
@@ -131,18 +157,25 @@ struct TcSlot {                          // per tile slot: shared-memory operand
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_forward_kernel(const TcPlan* __restrict__ P, const float* __restrict__ params, const float* __restrict__ node,
+tc_forward_kernel(const TcPlan* __restrict__ P, const float* __restrict__ wimg, const float* __restrict__ node,
                   const float* __restrict__ edge, const uint32_t* __restrict__ in_mask, float* __restrict__ q_out, int B,
                   float* __restrict__ dbg, int dbg_layer) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t ops_bar[2];        // operands of the slot's next layer are in place (512 arrivals)
+  __shared__ __align__(8) uint64_t ops_bar[2];        // operands of the slot's next layer are in place (16 warp arrivals)
   __shared__ __align__(8) uint64_t acc_bar[2];        // the slot's accumulator is complete (tcgen05.commit)
+  __shared__ __align__(8) uint64_t w_bar;             // the weight image has landed
   __shared__ uint32_t tmem_base_s;
+  struct LayerRt { int Kpad, Npad, relu, a_src, out_kind, dcol, acol, w_off, bias_off; };
+  __shared__ LayerRt lay[kTcMaxLayers];               // the per-layer scalars of the plan (the plan itself is in global memory)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = P->N, TG = P->TG, Dn = P->Dn, De = P->De, CH = P->CH, XP = P->x_planes, dn_pad = P->dn_pad;
   const int FP = P->F >> 2;                                   // planes of h / agg
   const int n_layers = P->n_layers;
   const int SP = P->stage_planes;                             // shared-memory operand planes per slot
+  if (tid < n_layers) {
+    const TcLayer& L = P->layers[tid];
+    lay[tid] = LayerRt{L.Kpad, L.Npad, L.relu, L.a_src, L.out_kind, L.dcol, L.acol, L.w_off, L.bias_off};
+  }
 
   float* Wsm = reinterpret_cast<float*>(smem);
   float* bias_s = Wsm + P->w_floats;
@@ -158,8 +191,9 @@ tc_forward_kernel(const TcPlan* __restrict__ P, const float* __restrict__ params
     }
   }
   if (tid == 0) {
-    mbar_init(&ops_bar[0], kTcEpiThreads); mbar_init(&ops_bar[1], kTcEpiThreads);
+    mbar_init(&ops_bar[0], kTcEpiThreads / 32); mbar_init(&ops_bar[1], kTcEpiThreads / 32);   // one arrival per epilogue warp
     mbar_init(&acc_bar[0], 1); mbar_init(&acc_bar[1], 1);
+    mbar_init(&w_bar, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_base_s, kTmemCols);
@@ -168,23 +202,15 @@ tc_forward_kernel(const TcPlan* __restrict__ P, const float* __restrict__ params
     const int nz = 2 * ((FP + 2 * SP) * kPlaneFloats + kTcRows);
     for (int i = tid; i < nz; i += kTcThreads) z[i] = 0.f;
   }
-  asm volatile("griddepcontrol.wait;" ::: "memory");          // parameters may come from the preceding optimiser kernel
-  // ---- weights: parameters -> hi/lo planes over k (K-major B operand), biases zero-padded
-  for (int l = 0; l < n_layers; ++l) {
-    const TcLayer& L = P->layers[l];
-    const int Kpad = L.Kpad, Npad = L.Npad, No = L.N;
-    float* Wc = Wsm + L.w_off;          // k-plane kc: rows [0, Npad) = hi(W[k][o]), rows [Npad, 2 Npad) = lo, 4 k's per row
-    for (int idx = tid; idx < Kpad * Npad; idx += kTcThreads) {
-      const int o = idx % Npad, k = idx / Npad;               // consecutive threads read consecutive o of one W row
-      const int wrow = L.kmap[k];
-      const float w = (wrow >= 0 && o < No) ? params[L.pw_off + wrow * No + o] : 0.f;
-      const float h = tf32_rn(w);
-      const int at = (k >> 2) * (2 * Npad * 4) + o * 4 + (k & 3);
-      Wc[at] = h;
-      Wc[at + Npad * 4] = tf32_rn(w - h);
-    }
-    for (int o = tid; o < Npad; o += kTcThreads) bias_s[L.bias_off + o] = (o < No) ? params[L.pb_off + o] : 0.f;
+  asm volatile("griddepcontrol.wait;" ::: "memory");          // the weight image comes from tc_stage_weights_kernel
+  // ---- weights + biases: one bulk-async copy of the pre-built image (written through the async proxy: no fence needed
+  //      before the tensor core reads it)
+  if (tid == 0) {
+    const uint32_t bytes = (uint32_t)((P->w_floats + P->bias_floats) * sizeof(float));
+    mbar_arrive_expect_tx(&w_bar, bytes);
+    bulk_g2s(Wsm, wimg, bytes, &w_bar);
   }
+  mbar_wait(&w_bar, 0u);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   fence_async_smem();
   tc_fence_before();
@@ -202,11 +228,10 @@ tc_forward_kernel(const TcPlan* __restrict__ P, const float* __restrict__ params
       for (int tA = blockIdx.x; tA < num_tiles; tA += 2 * G) {
         const bool validB = tA + G < num_tiles;
         for (int l = 0; l < n_layers; ++l) {
-          const TcLayer& L = P->layers[l];
-          const int Kpad = L.Kpad, Npad = L.Npad;
+          const int Kpad = lay[l].Kpad, Npad = lay[l].Npad, a_src = lay[l].a_src, dcol = lay[l].dcol, acol = lay[l].acol;
           const uint32_t idesc2 = umma_idesc_tf32(2 * Npad), idesc1 = umma_idesc_tf32(Npad);
           const uint32_t b_plane = (uint32_t)(2 * Npad * 16);             // one k-plane of W: 2 Npad rows x 16 bytes
-          const uint64_t db0 = umma_desc(smem_u32(Wsm + L.w_off), b_plane, 128);
+          const uint64_t db0 = umma_desc(smem_u32(Wsm + lay[l].w_off), b_plane, 128);
           const uint64_t b_step = (uint64_t)((2 * b_plane) >> 4);
           const int ksteps = Kpad >> 3;
 #pragma unroll
@@ -216,17 +241,17 @@ tc_forward_kernel(const TcPlan* __restrict__ P, const float* __restrict__ params
             po[s] ^= 1u;
             tc_fence_after();
             const uint32_t tslot = tmem_base + (uint32_t)(s * kSlotCols);
-            const uint32_t d_t = tslot + (uint32_t)L.dcol;
+            const uint32_t d_t = tslot + (uint32_t)dcol;
             uint64_t db = db0;
             // per k-step (8 of K): D[:, 0:2Npad] += A_hi * [W_hi | W_lo]  and  D[:, 0:Npad] += A_lo * W_hi
-            if (L.a_src == 2) {                               // operand in tensor memory (written by the previous epilogue)
-              uint32_t ah = tslot + (uint32_t)L.acol, al = ah + (uint32_t)Kpad;
+            if (a_src == 2) {                                 // operand in tensor memory (written by the previous epilogue)
+              uint32_t ah = tslot + (uint32_t)acol, al = ah + (uint32_t)Kpad;
               for (int ks = 0; ks < ksteps; ++ks, ah += 8u, al += 8u, db += b_step) {
                 tc_mma_tf32_ts(d_t, ah, db, idesc2, ks > 0 ? 1u : 0u);
                 tc_mma_tf32_ts(d_t, al, db, idesc1, 1u);
               }
             } else {
-              const uint32_t a_off = (uint32_t)((L.a_src == 0 ? x_plane0 : 0) * kPlaneBytes);
+              const uint32_t a_off = (uint32_t)((a_src == 0 ? x_plane0 : 0) * kPlaneBytes);
               uint64_t dah = umma_desc(smem_u32(slot[s].stage_hi) + a_off, kPlaneBytes, 128);
               uint64_t dal = umma_desc(smem_u32(slot[s].stage_lo) + a_off, kPlaneBytes, 128);
               const uint64_t a_step = (uint64_t)((2 * kPlaneBytes) >> 4);
@@ -278,7 +303,8 @@ tc_forward_kernel(const TcPlan* __restrict__ P, const float* __restrict__ params
       }
       if (tid < TG * N) slot[s].mask_s[tid] = min_[s];
       fence_async_smem();
-      mbar_arrive(&ops_bar[s]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ops_bar[s]);
       fetch(s, next_tile);
     };
     fetch(0, blockIdx.x);
@@ -288,9 +314,8 @@ tc_forward_kernel(const TcPlan* __restrict__ P, const float* __restrict__ params
       start_tile(0, tA + 2 * G);
       if (validB) start_tile(1, tA + 3 * G);
       for (int l = 0; l < n_layers; ++l) {
-        const TcLayer& L = P->layers[l];
-        const int Npad = L.Npad;
-        const float* bs = bias_s + L.bias_off;
+        const int Npad = lay[l].Npad, relu = lay[l].relu, out_kind = lay[l].out_kind, dcol = lay[l].dcol;
+        const float* bs = bias_s + lay[l].bias_off;
         // columns are dealt to the 4 column quarters in 8-column chunks: chunk j of this thread = 8 * (cq + 4 j)
         const int nch = ((Npad >> 3) - cq + 3) >> 2;          // <= 3 for Npad <= 96
 #pragma unroll
@@ -300,7 +325,7 @@ tc_forward_kernel(const TcPlan* __restrict__ P, const float* __restrict__ params
           const int g0 = tile * TG;
           const int R = min(TG, B - g0) * N;
           const TcSlot& S = slot[s];
-          const uint32_t t_d = t_lane + (uint32_t)(s * kSlotCols + L.dcol);
+          const uint32_t t_d = t_lane + (uint32_t)(s * kSlotCols + dcol);
           mbar_wait(&acc_bar[s], pa[s]);
           pa[s] ^= 1u;
           tc_fence_after();
@@ -327,10 +352,10 @@ tc_forward_kernel(const TcPlan* __restrict__ P, const float* __restrict__ params
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 v[i] += bs[c0 + i];
-                if (L.relu) v[i] = fmaxf(v[i], 0.f);
+                if (relu) v[i] = fmaxf(v[i], 0.f);
               }
               const float4 x0 = make_float4(v[0], v[1], v[2], v[3]), x1 = make_float4(v[4], v[5], v[6], v[7]);
-              if (L.out_kind == 2) {
+              if (out_kind == 2) {
                 if (row < R) {
                   float* qd = q_out + ((size_t)g0 * N + row) * CH;
 #pragma unroll
@@ -341,7 +366,7 @@ tc_forward_kernel(const TcPlan* __restrict__ P, const float* __restrict__ params
                 float4 h0, l0, h1, l1;
                 split4(x0, h0, l0);
                 split4(x1, h1, l1);
-                if (L.out_kind == 1) {                       // MLP chain: back into tensor memory, over the accumulator
+                if (out_kind == 1) {                         // MLP chain: back into tensor memory, over the accumulator
                   tc_st8(t_d + (uint32_t)c0, h0, h1);
                   tc_st8(t_d + (uint32_t)(Npad + c0), l0, l1);
                 } else {                                     // combine stage: fp32 copy for the aggregation + operand planes
@@ -357,7 +382,7 @@ tc_forward_kernel(const TcPlan* __restrict__ P, const float* __restrict__ params
             }
           }
           // ---- neighbour aggregation after a combine stage: agg[pc][g, m] = sum_n Adj[g][n][m] * h[pc][g, n]  -> hi / lo planes
-          if (L.out_kind == 0) {
+          if (out_kind == 0) {
             epi_barrier();
             const int items = FP * TG * MS;
             for (int item = tid; item < items; item += kTcEpiThreads) {
@@ -386,10 +411,11 @@ tc_forward_kernel(const TcPlan* __restrict__ P, const float* __restrict__ params
               *reinterpret_cast<float4*>(S.stage_lo + at) = lo;
             }
           }
-          if (L.out_kind != 2) {                              // hand the next layer's operands to the MMA warp
-            if (L.out_kind == 1) tc_wait_st(); else fence_async_smem();
+          if (out_kind != 2) {                                // hand the next layer's operands to the MMA warp
+            if (out_kind == 1) tc_wait_st(); else fence_async_smem();
             tc_fence_before();
-            mbar_arrive(&ops_bar[s]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ops_bar[s]);
           }
         }
       }
@@ -496,24 +522,34 @@ int tc_build_plan(const TcShape& s, TcPlan* out) {
 
 int tc_grid(const TcPlan& p, int B) { return std::max(1, std::min(ceil_div(B, p.TG), sm_count())); }
 
-int tc_forward_launch(const TcPlan& ph, const TcPlan* plan_dev, const float* params, const float* node, const float* edge,
-                      const uint32_t* in_mask, float* q_out, int B, cudaStream_t st, float* dbg, int dbg_layer) {
+int tc_forward_launch(const TcPlan& ph, const TcPlan* plan_dev, const float* params, float* wimg, const float* node,
+                      const float* edge, const uint32_t* in_mask, float* q_out, int B, cudaStream_t st, float* dbg, int dbg_layer) {
   static int smem_set = 0;
   if (ph.smem_bytes > smem_set) {
     V2V_CHECK_CUDA(cudaFuncSetAttribute(tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ph.smem_bytes));
     smem_set = ph.smem_bytes;
+  }
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  {
+    cudaLaunchConfig_t ls{};
+    ls.gridDim = dim3(24);
+    ls.blockDim = dim3(256);
+    ls.stream = st;
+    ls.attrs = attr;
+    ls.numAttrs = 1;
+    V2V_CHECK_CUDA(cudaLaunchKernelEx(&ls, tc_stage_weights_kernel, plan_dev, params, wimg));
+    if (int rc = launch_status("tc_stage_weights_kernel")) return rc;
   }
   cudaLaunchConfig_t lc{};
   lc.gridDim = dim3(tc_grid(ph, B));
   lc.blockDim = dim3(kTcThreads);
   lc.dynamicSmemBytes = ph.smem_bytes;
   lc.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = attr;
   lc.numAttrs = 1;
-  V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, tc_forward_kernel, plan_dev, params, node, edge, in_mask, q_out, B, dbg, dbg_layer));
+  V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, tc_forward_kernel, plan_dev, (const float*)wimg, node, edge, in_mask, q_out, B, dbg, dbg_layer));
   return launch_status("tc_forward_kernel");
 }
 

@@ -45,7 +45,8 @@ struct TcShape {
 // Builds the plan; returns non-zero (with last_error) when the configuration is outside the tensor-core path.
 int tc_build_plan(const TcShape& s, TcPlan* out);
 int tc_grid(const TcPlan& p, int B);
-int tc_forward_launch(const TcPlan& plan_host, const TcPlan* plan_dev, const float* params, const float* node,
+// wimg: device scratch of (w_floats + bias_floats) floats for the staged weight image (rebuilt by every call)
+int tc_forward_launch(const TcPlan& plan_host, const TcPlan* plan_dev, const float* params, float* wimg, const float* node,
                       const float* edge, const uint32_t* in_mask, float* q_out, int B, cudaStream_t st, float* dbg = nullptr,
                       int dbg_layer = -1);
 

@@ -172,7 +172,7 @@ int v2v_brain_set_fused(v2v_brain* b, int enable);
  * feature rows, shared-memory bytes, phases, weight-gradient blocks, bias slots, table entries}. */
 int v2v_brain_fused_info(v2v_brain* b, int B, int train, int* info8);
 /* predict on the tensor cores (csrc/tc_forward.cu: tcgen05.mma kind::tf32, 3 passes per contraction = fp32-grade
- * products, accumulators in TMEM): mode 0 never, 1 automatic (default: batches that give every SM >= 4 tiles of 128 node
+ * products, accumulators in TMEM): mode 0 never, 1 automatic (default: batches that give every SM >= 2 tiles of 128 node
  * rows), 2 whenever the brain is capable (shared weights, N <= 32, binary adjacency, zero neighbour input).
  * info4 = {capable, mode, graphs per tile, shared-memory bytes}.  Environment override at creation: V2V_TENSOR_CORE. */
 int v2v_brain_set_tensor_core(v2v_brain* b, int mode);
