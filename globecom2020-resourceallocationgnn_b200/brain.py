@@ -117,6 +117,7 @@ class BS:
         self._handle = None
         self._max_batch = 0
         self._pin = {}
+        self._loss_keys = [f"D{k + 1}_Decide_Output_loss" for k in range(int(num_d2d))]
         if data_parallel is None:
             data_parallel = torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1
@@ -544,7 +545,7 @@ class BS:
                 N = self.num_D2D
                 hl = np.empty(N, np.float32)
                 hist = History()
-                keys = [f"D{k + 1}_Decide_Output_loss" for k in range(N)]
+                keys = self._loss_keys
                 hist.history = {"loss": [], **{k: [] for k in keys}}
                 for ep in range(int(epochs)):
                     if self._comm is not None:       # data parallel: this rank's rows, fused NVLink exchange + Adam
@@ -554,11 +555,11 @@ class BS:
                         rc = self._lib.v2v_brain_train_views(self._handle, na, nn, ea, en, ga, gn, aa, an, ya, yn, B,
                                                              hl.ctypes.data, _lib.current_stream())
                     _lib.check(rc, ValueError)
-                    per_head = hl.astype(np.float64)
+                    per_head = hl.astype(np.float64).tolist()
                     hist.epoch.append(ep)
-                    hist.history["loss"].append(float(per_head.sum()))
+                    hist.history["loss"].append(float(sum(per_head)))
                     for k in range(N):
-                        hist.history[keys[k]].append(float(per_head[k]))
+                        hist.history[keys[k]].append(per_head[k])
                 return hist
         B, node, edge, neigh, adj = self._pack_inputs(x)
         ylab = self._pack_labels(y, B)

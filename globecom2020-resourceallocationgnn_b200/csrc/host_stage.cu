@@ -105,7 +105,8 @@ class StagePool {
     if (hw <= 0) hw = 4;
     int local_world = 1;
     if (const char* e = getenv("LOCAL_WORLD_SIZE")) local_world = std::max(1, atoi(e));
-    int n = std::min(8, std::max(1, hw / (2 * local_world))) - (local_world > 1 ? 1 : 0);   // the caller works as well
+    // the caller works as well: with several ranks per host every rank gets its share of the cores minus its own thread
+    int n = local_world > 1 ? std::min(8, std::max(1, hw / local_world)) - 1 : std::min(8, std::max(1, hw / 2));
     if (const char* e = getenv("V2V_HOST_THREADS")) n = std::max(0, std::min(64, atoi(e)));
     n_threads_ = n;
     for (int i = 0; i < n; ++i) std::thread([this] { loop(); }).detach();
