@@ -110,6 +110,11 @@ SIGNATURES = {
                                         C.c_int, c_view_p, C.c_int, C.c_int, c_void_p, c_void_p]),
     "v2v_brain_train_views_dp": (C.c_int, [c_void_p, c_void_p, c_view_p, C.c_int, c_view_p, C.c_int, c_view_p, C.c_int,
                                            c_view_p, C.c_int, c_view_p, C.c_int, C.c_int, c_void_p, c_void_p]),
+    "v2v_env_renew_channels": (C.c_int, [c_void_p] * 11 + [C.c_int, C.c_int, C.c_int, c_void_p]),
+    "v2v_env_pack_state": (C.c_int, [c_void_p] * 8 + [C.c_int, C.c_int, C.c_int, c_void_p]),
+    "v2v_env_reward": (C.c_int, [c_void_p] * 9 + [C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, c_void_p]),
+    "v2v_env_renew_positions": (C.c_int, [c_void_p] * 4 + [C.c_int, C.c_int, c_void_p]),
+    "v2v_env_choose_destinations": (C.c_int, [c_void_p] * 3 + [C.c_int, C.c_int, c_void_p]),
     "v2v_host_stage_threads": (C.c_int, []),
     "v2v_brain_set_tensor_core": (C.c_int, [c_void_p, C.c_int]),
     "v2v_brain_tensor_core_info": (C.c_int, [c_void_p, c_i32_p]),

@@ -250,6 +250,32 @@ int v2v_host_pack_adjacency(const v2v_host_view* adj_view, int B, int N, uint32_
                             int* flags_out);
 
 /* ------------------------------------------------------------------------
+ * Batched environment: E independent copies of the reference simulator stepped on the device, state in
+ * HBM, fp32.  Randomness is INJECTED (arrays of draws) so that every kernel is checked against vectors recorded from the
+ * unmodified Environment.py.  Layouts: pos [E][N][2] (x, y), dir [E][N] (0 up, 1 down, 2 left, 3 right), vel [E][N],
+ * v2v_shadow [E][N][N], v2i_shadow [E][N], dest [E][N], v2v_ff [E][N][N][RB] (= V2V_channels_with_fastfading),
+ * v2i_ff [E][N][RB], v2i_abs [E][N].
+ *  - renew_channels (Environment.py:378-404 with :63-120, :140-165): z_v2v [E][N][N] ~ N(0, 3), z_v2i [E][N] ~ N(0, 8) are
+ *    the shadowing draws, ff_v2v [E][N][N][RB][2] / ff_v2i [E][N][RB][2] the standard-normal (re, im) fast-fading draws.
+ *  - pack_state (BS_brain.py:389-407, :441-469): node [E][N][2RB+1], edge [E][N][RB], the adjacency as bit masks
+ *    (N <= 32; both or neither) and/or dense adj [E][N][N] (may be NULL).
+ *  - reward (Environment.py:406-458; BS_brain.py:515-519): per-link V2V rates [E][N], V2I rates [E][min(RB,N)], the V2I
+ *    interference [E][RB] and reward[e] = v2v_weight * sum(V2V) + v2i_weight * sum(V2I); outputs may be NULL.  N <= 32.
+ *  - renew_positions (Environment.py:236-345): u [E][N] = the uniform draw a vehicle uses if it reaches a crossing.
+ *  - choose_destinations (Environment.py:360-376): receiver = candidate floor(u (N-3)) of the other vehicles by distance,
+ *    the two farthest excluded. */
+int v2v_env_renew_channels(const float* pos, const float* vel, float* v2v_shadow, float* v2i_shadow, const float* z_v2v,
+                           const float* z_v2i, const float* ff_v2v, const float* ff_v2i, float* v2v_ff, float* v2i_ff,
+                           float* v2i_abs, int E, int N, int RB, void* stream);
+int v2v_env_pack_state(const int* dest, const float* v2v_ff, const float* v2i_ff, float* node, float* edge,
+                       uint32_t* in_mask, uint32_t* out_mask, float* adj, int E, int N, int RB, void* stream);
+int v2v_env_reward(const int* actions, const int* dest, const float* v2v_ff, const float* v2i_ff, const float* v2i_abs,
+                   float* v2v_rate, float* v2i_rate, float* interference, float* reward, float v2v_weight, float v2i_weight,
+                   int E, int N, int RB, void* stream);
+int v2v_env_renew_positions(float* pos, int* dir, const float* vel, const float* u, int E, int N, void* stream);
+int v2v_env_choose_destinations(const float* pos, const float* u, int* dest, int E, int N, void* stream);
+
+/* ------------------------------------------------------------------------
  * Data parallelism (one process per GPU).  The reference has no distributed path; every batch row is an
  * independent graph, so ranks own contiguous batch shards and exchange ONE flat gradient per step.
  * v2v_comm is that exchange over NVLink peer memory (cudaIpc): create one per rank with the payload size

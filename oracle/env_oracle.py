@@ -4,7 +4,7 @@ TEST INFRASTRUCTURE ONLY (same import rules as oracle/v2v_oracle.py): only tests
 bench.py's cpu_baseline leg may import it.  Every function cites the lines of /root/reference/Environment.py (or
 BS_brain.py) it follows; the reference runs in this image, so the restatement is PINNED: tests/golden/make_env_golden.py
 drives the unmodified Environment.Environ, copies its state into these functions and stores inputs and the reference's
-own outputs in tests/golden/env_*.npz (tests/test_env_oracle.py checks them to 1e-12, fp64).
+own outputs in tests/golden/sim_*.npz (tests/test_env_oracle.py checks them to 1e-12, fp64).
 
 Randomness is INJECTED: the reference fills its Gaussian arrays element by element from Python's `random.gauss`
 (Environment.py:14-42) and draws `random.uniform` lazily at lane crossings (:251, :259, ...); here every function takes

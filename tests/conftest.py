@@ -15,7 +15,8 @@ def pytest_configure(config):
 
 
 def golden_cases():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+    # brain cases only: the simulator recordings (sim_*.npz, tests/golden/make_env_golden.py) have their own tests
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith("sim_"))
 
 
 @pytest.fixture(scope="session")

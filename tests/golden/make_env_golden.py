@@ -139,7 +139,7 @@ def neighbor_case(seed):
         z = np.array([[complex(c.position[0], c.position[1]) for c in env.vehicles]])
         dist = abs(z.T - z)
         cand = np.stack([np.argsort(dist[:, i])[1:n - 2] for i in range(n)])                # Environment.py:370-374
-        np.savez_compressed(os.path.join(os.path.dirname(__file__), f"env_neighbors_n{n}.npz"),
+        np.savez_compressed(os.path.join(os.path.dirname(__file__), f"sim_neighbors_n{n}.npz"),
                             pos=np.array([v.position for v in env.vehicles], float), cand=cand,
                             dest=np.array([v.destinations[0] for v in env.vehicles]))
 
@@ -147,7 +147,7 @@ def neighbor_case(seed):
 if __name__ == "__main__":
     here = os.path.dirname(os.path.abspath(__file__))
     for n, seed in ((4, 1001), (8, 7), (20, 1001)):
-        np.savez_compressed(os.path.join(here, f"env_steps_n{n}.npz"), **channel_case(n, seed))
-    np.savez_compressed(os.path.join(here, "env_mobility.npz"), **mobility_case(3))
+        np.savez_compressed(os.path.join(here, f"sim_steps_n{n}.npz"), **channel_case(n, seed))
+    np.savez_compressed(os.path.join(here, "sim_mobility.npz"), **mobility_case(3))
     neighbor_case(11)
     print("written")

@@ -17,7 +17,7 @@ def load(name):
 
 @pytest.mark.parametrize("n", [4, 8, 20])
 def test_channels_rewards_state_match_reference(n):
-    z = load(f"env_steps_n{n}.npz")
+    z = load(f"sim_steps_n{n}.npz")
     T = z["pos"].shape[0]
     # the step: channels from the positions AFTER the move, shadows before the update, the reference's own draws
     sh_v, sh_i, v2v_ff, v2i_ff, v2v_abs, v2i_abs = EO.renew_channels(z["pos1"], z["vel"], z["v2v_shadow0"], z["v2i_shadow0"], z["z_v2v"],
@@ -40,7 +40,7 @@ def test_channels_rewards_state_match_reference(n):
 
 
 def test_mobility_matches_reference():
-    z = load("env_mobility.npz")
+    z = load("sim_mobility.npz")
     cross = EO.crossing(z["pos"], z["dir"], z["vel"])
     # the reference draws lazily, in vehicle order: hand every crossing vehicle its draw
     u = np.ones(cross.shape)
@@ -56,7 +56,7 @@ def test_mobility_matches_reference():
 
 @pytest.mark.parametrize("n", [4, 8, 20])
 def test_destination_candidates_match_reference(n):
-    z = load(f"env_neighbors_n{n}.npz")
+    z = load(f"sim_neighbors_n{n}.npz")
     cand = EO.destination_candidates(z["pos"][None])[0]
     assert np.array_equal(cand, z["cand"])
     assert all(z["dest"][i] in cand[i] for i in range(n))                     # the reference's sampled receiver is a candidate
@@ -67,7 +67,7 @@ def test_destination_candidates_match_reference(n):
 def test_steps_mobility_in_recorded_episodes():
     """The ordinary (crossing-free) moves of the recorded episodes."""
     for n in (4, 8, 20):
-        z = load(f"env_steps_n{n}.npz")
+        z = load(f"sim_steps_n{n}.npz")
         cross = EO.crossing(z["pos"], z["dir"], z["vel"])
         u = np.ones(cross.shape)
         for t in range(cross.shape[0]):

@@ -1,0 +1,124 @@
+"""Batched environment kernels (csrc/env.cu) against golden vectors recorded from the unmodified reference simulator and
+against the vectorised oracle; plus full-size properties and a device-resident transition -> brain step."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import env_oracle as EO
+
+pytestmark = pytest.mark.gpu
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLDEN, name)))
+
+
+def dev(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to("cuda", dtype=dtype)
+
+
+def make_env(v2v, T, n):
+    env = v2v.BatchedEnviron(T, n_veh=n, n_rb=4, seed=1)
+    return env
+
+
+@pytest.mark.parametrize("n", [4, 8, 20])
+def test_channels_rewards_state_against_reference_recording(v2v, n):
+    """Every recorded step of the reference is one 'environment' of the batch."""
+    z = load(f"sim_steps_n{n}.npz")
+    T = z["pos"].shape[0]
+    env = make_env(v2v, T, n)
+    env.pos.copy_(dev(z["pos1"])); env.vel.copy_(dev(z["vel"]))
+    env.v2v_shadow.copy_(dev(z["v2v_shadow0"])); env.v2i_shadow.copy_(dev(z["v2i_shadow0"]))
+    env.renew_channels_fastfading(dev(z["z_v2v"]), dev(z["z_v2i"]), dev(z["ff_v2v"]), dev(z["ff_v2i"]))
+    nxt_v = np.concatenate([z["v2v_ff"][1:], z["v2v_ff_last"]])
+    nxt_i = np.concatenate([z["v2i_ff"][1:], z["v2i_ff_last"]])
+    # dB values around 100: fp32 arithmetic, 2e-4 dB absolute
+    assert np.abs(env.V2V_channels_with_fastfading.cpu().numpy() - nxt_v).max() <= 2e-4
+    assert np.abs(env.V2I_channels_with_fastfading.cpu().numpy() - nxt_i).max() <= 2e-4
+    assert np.abs(env.v2v_shadow.cpu().numpy() - z["v2v_shadow1"]).max() <= 1e-5
+    assert np.abs(env.v2i_shadow.cpu().numpy() - z["v2i_shadow1"]).max() <= 1e-5
+    # rewards and state on the recorded (reference) channels
+    env.V2V_channels_with_fastfading.copy_(dev(z["v2v_ff"])); env.V2I_channels_with_fastfading.copy_(dev(z["v2i_ff"]))
+    env.V2I_channels_abs.copy_(dev(z["v2i_abs"])); env.dest.copy_(dev(z["dest"], torch.int32))
+    v2v_rate, v2i_rate, interf, reward = env.compute_reward_with_channel_selection(dev(z["actions"], torch.int32), 1.0, 0.1)
+    assert np.abs(v2v_rate.cpu().numpy() - z["v2v_rate"]).max() <= 1e-4 * max(1.0, np.abs(z["v2v_rate"]).max())
+    assert np.abs(v2i_rate.cpu().numpy() - z["v2i_rate"]).max() <= 1e-4 * max(1.0, np.abs(z["v2i_rate"]).max())
+    assert np.all(np.abs(interf.cpu().numpy() - z["interference"]) <= 1e-4 * np.abs(z["interference"]) + 1e-30)
+    want_r = z["v2v_rate"].sum(1) + 0.1 * z["v2i_rate"].sum(1)
+    assert np.abs(reward.cpu().numpy() - want_r).max() <= 1e-4 * np.abs(want_r).max()
+    node, edge, im, om, adj = env.pack_state(dense_adj=True)
+    assert np.abs(node.cpu().numpy() - z["node"]).max() <= 1e-5 and np.abs(edge.cpu().numpy() - z["edge"]).max() <= 1e-5
+    assert np.array_equal(adj.cpu().numpy(), z["adj"])
+    rim, rom, binary = v2v.pack_adjacency(dev(z["adj"]))                      # bit-exact against the adjacency packer
+    assert binary and torch.equal(im, rim) and torch.equal(om, rom)
+
+
+def test_mobility_against_reference_recording(v2v):
+    z = load("sim_mobility.npz")
+    cross = EO.crossing(z["pos"], z["dir"], z["vel"])
+    u = np.ones(cross.shape)
+    for t in range(cross.shape[0]):
+        u[t, cross[t]] = z["u"][t][~np.isnan(z["u"][t])]
+    T, n = z["dir"].shape
+    env = make_env(v2v, T, n)
+    env.pos.copy_(dev(z["pos"])); env.dir.copy_(dev(z["dir"], torch.int32)); env.vel.copy_(dev(z["vel"]))
+    env.renew_positions(dev(u))
+    assert np.array_equal(env.dir.cpu().numpy(), z["dir1"])
+    assert np.abs(env.pos.cpu().numpy() - z["pos1"]).max() <= 2e-4           # fp32 metres on a 1299 m map
+
+
+@pytest.mark.parametrize("n", [4, 8, 20])
+def test_destinations_against_reference_recording(v2v, n):
+    z = load(f"sim_neighbors_n{n}.npz")
+    cand = z["cand"]
+    K = cand.shape[1]
+    env = make_env(v2v, K, n)
+    env.pos.copy_(dev(np.repeat(z["pos"][None], K, 0)))
+    u = (np.arange(K)[:, None] + 0.5) / K * np.ones((K, n))                   # environment k picks candidate k
+    env.renew_neighbor(dev(u))
+    assert np.array_equal(env.dest.cpu().numpy(), cand.T)
+
+
+def test_full_size_properties_and_brain_step(v2v):
+    """BASELINE-size batch (8192 environments x 20 vehicles): oracle on a slice, invariants on everything, and one
+    device-resident transition -> TD target -> train step with no host round trip of the state."""
+    E, N = 8192, 20
+    env = v2v.BatchedEnviron(E, n_veh=N, n_rb=4, seed=1001)
+    env.new_random_game()
+    pos0 = env.pos.clone()
+    for _ in range(3):
+        env.renew_positions(); env.renew_channels_fastfading()
+    assert float((env.pos - pos0).abs().max()) <= 3 * 0.15 + 1e-3 + 1299     # moves are <= 0.15 m unless wrapped at the border
+    assert bool(((env.pos[..., 0] >= 0) & (env.pos[..., 0] <= 750) & (env.pos[..., 1] >= 0) & (env.pos[..., 1] <= 1299)).all())
+    d = env.dest.cpu().numpy()
+    assert (d != np.arange(N)[None]).all() and d.min() >= 0 and d.max() < N
+    node, edge, im, om, adj = env.pack_state(dense_adj=True)
+    assert torch.isfinite(node).all() and torch.isfinite(edge).all()
+    assert torch.all(adj.sum(1) == N - 2)                                     # in-degree N-2 (BS_brain.py:441-445)
+    sl = slice(100, 132)
+    no, eo, ao = EO.pack_state(d[sl], env.V2V_channels_with_fastfading[sl].double().cpu().numpy(),
+                               env.V2I_channels_with_fastfading[sl].double().cpu().numpy())
+    assert np.abs(node[sl].cpu().numpy() - no).max() <= 1e-5 and np.abs(edge[sl].cpu().numpy() - eo).max() <= 1e-5
+    actions = torch.randint(0, 4, (E, N), device="cuda", dtype=torch.int32)
+    v2v_rate, v2i_rate, interf, reward = env.compute_reward_with_channel_selection(actions)
+    ro = EO.compute_reward(actions[sl].cpu().numpy(), d[sl], env.V2V_channels_with_fastfading[sl].double().cpu().numpy(),
+                           env.V2I_channels_with_fastfading[sl].double().cpu().numpy(), env.V2I_channels_abs[sl].double().cpu().numpy())
+    assert np.abs(v2v_rate[sl].cpu().numpy() - ro[0]).max() <= 1e-4 * max(1.0, np.abs(ro[0]).max())
+    assert torch.isfinite(reward).all() and float(reward.min()) >= 0.0
+    # transition -> brain, all on the device
+    brain = v2v.BS(N, 3, 1, 16, 1, 4, stages=2, per_slot=False, max_batch=E, data_parallel=False, seed=3)
+    brain.update_target_model()
+    q = brain.forward_device(node, edge, in_mask=im)
+    env.renew_positions(); env.renew_channels_fastfading()
+    node2, edge2, _, _ = env.pack_state()
+    q2 = brain.forward_device(node2, edge2, in_mask=im, target=True)
+    y = torch.empty_like(q)
+    lib = brain._lib
+    v2v._lib.check(lib.v2v_td_target(q.data_ptr(), q2.data_ptr(), actions.data_ptr(), reward.data_ptr(), 0.5, y.data_ptr(), E, N, 4,
+                                     v2v._lib.current_stream()))
+    hl = brain.train_step_device(node, edge, im, om, None, y)
+    assert torch.isfinite(hl).all()
