@@ -202,13 +202,15 @@ tc_forward_kernel(const TcPlan* __restrict__ P, const float* __restrict__ wimg, 
     const int nz = 2 * ((FP + 2 * SP) * kPlaneFloats + kTcRows);
     for (int i = tid; i < nz; i += kTcThreads) z[i] = 0.f;
   }
+  __syncthreads();                                            // the mbarrier inits are visible to every waiting thread
   asm volatile("griddepcontrol.wait;" ::: "memory");          // the weight image comes from tc_stage_weights_kernel
   // ---- weights + biases: one bulk-async copy of the pre-built image (written through the async proxy: no fence needed
   //      before the tensor core reads it)
   if (tid == 0) {
     const uint32_t bytes = (uint32_t)((P->w_floats + P->bias_floats) * sizeof(float));
     mbar_arrive_expect_tx(&w_bar, bytes);
-    bulk_g2s(Wsm, wimg, bytes, &w_bar);
+    for (uint32_t off = 0; off < bytes; off += 32768u)         // in 32 KB pieces
+      bulk_g2s(reinterpret_cast<uint8_t*>(Wsm) + off, reinterpret_cast<const uint8_t*>(wimg) + off, min(32768u, bytes - off), &w_bar);
   }
   mbar_wait(&w_bar, 0u);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
