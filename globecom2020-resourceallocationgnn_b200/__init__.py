@@ -12,10 +12,10 @@ from . import _lib, build                                     # noqa: F401
 from ._lib import V2VError, load as load_library, lib_path    # noqa: F401
 from .layers import GNNLayer, AggLayer, aggregate, pack_adjacency, adjacency_from_input, dense_forward  # noqa: F401
 from .brain import BS, History                                # noqa: F401
-from .dqn import Agent, ReplayRing, pack_state, get_state     # noqa: F401
+from .dqn import Agent, BatchedAgent, ReplayRing, pack_state, get_state     # noqa: F401
 from .env import BatchedEnviron                                # noqa: F401
 
-__all__ = ["GNNLayer", "AggLayer", "BS", "History", "Agent", "ReplayRing", "BatchedEnviron", "pack_state", "get_state", "aggregate", "pack_adjacency", "adjacency_from_input",
+__all__ = ["GNNLayer", "AggLayer", "BS", "History", "Agent", "BatchedAgent", "ReplayRing", "BatchedEnviron", "pack_state", "get_state", "aggregate", "pack_adjacency", "adjacency_from_input",
            "dense_forward", "load_library", "lib_path", "V2VError", "huber_loss"]
 
 

@@ -83,6 +83,20 @@ class ReplayRing:
         self.head = int((self.head + T) % self.capacity)
         self.size = min(self.capacity, self.size + T)
 
+    def add_device(self, node, edge, in_mask, out_mask, action, reward, node_, edge_):
+        """Append T transitions that already live on the device (the batched environment's output): no host copy."""
+        T = int(reward.shape[0])
+        if T == 0:
+            return
+        if T > self.capacity:
+            raise ValueError("more transitions than the ring holds")
+        idx = (self.head + torch.arange(T, device=self.device)) % self.capacity
+        for dst, src in ((self.node, node), (self.edge, edge), (self.node_, node_), (self.edge_, edge_), (self.in_mask, in_mask),
+                         (self.out_mask, out_mask), (self.action, action.to(torch.int32)), (self.reward, reward)):
+            dst.index_copy_(0, idx, src.reshape((T,) + tuple(dst.shape[1:])))
+        self.head = int((self.head + T) % self.capacity)
+        self.size = min(self.capacity, self.size + T)
+
     def sample_indices(self, n, rng=np.random):
         """Memory.sample (:258-270): without replacement when enough samples exist, else with replacement."""
         if self.size >= n:
@@ -264,3 +278,98 @@ class Agent:
                 v2v_rate, v2i_rate, _ = self.act(action.copy())
                 out[ep, t] = self.v2v_weight * np.sum(np.sum(v2v_rate, axis=1)) + self.v2i_weight * np.sum(v2i_rate)
         return out
+
+
+class BatchedAgent:
+    """The reference DQN loop (BS_brain.py:409-553 transitions, :555-748 replay, :750-910 episodes) over E environments
+    at once, entirely on the device: ``BatchedEnviron`` (csrc/env.cu) produces states and rewards, the brain acts on
+    them with ``forward_device``, transitions go into the ``ReplayRing`` by index copy, and ``replay`` is the same
+    device-side step as ``Agent.replay``.  One call of ``generate_transitions(T)`` adds E*T transitions.
+
+    Action selection follows :308-352 per environment: with probability epsilon (linear anneal, :315-324) all N links of
+    that environment draw a uniform random channel, otherwise each link takes the first maximiser of its Q row.
+    """
+
+    def __init__(self, environment, curr_rl_config, num_d2d_feedback=16, memory_capacity=1 << 18, seed=None, **brain_kwargs):
+        self.env = environment
+        self.num_D2D, self.num_CH, self.num_Neighbor = environment.n_Veh, environment.n_RB, 1
+        self.E = environment.E
+        self.epsilon, self.num_step = MAX_EPSILON, 0
+        brain_kwargs.setdefault("max_batch", max(curr_rl_config.Batch_Size, self.E))
+        self.brain = BS(self.num_D2D, 3, 1, num_d2d_feedback, 1, self.num_CH, **brain_kwargs)
+        self.batch_size, self.gamma = curr_rl_config.Batch_Size, curr_rl_config.Gamma
+        self.v2v_weight, self.v2i_weight = curr_rl_config.v2v_weight, curr_rl_config.v2i_weight
+        self.memory = ReplayRing(memory_capacity, self.num_D2D, self.brain.num_One_Node_Input, self.brain.num_One_Edge_Input,
+                                 device=environment.dev)
+        self.total_steps = 1
+        self.gen = torch.Generator(device=environment.dev)
+        if seed is not None:
+            self.gen.manual_seed(int(seed))
+        self._lib = _lib.load()
+
+    def _update_epsilon(self):
+        steps = 0.8 * self.total_steps                                                   # :315-324
+        per_step = (MAX_EPSILON - MIN_EPSILON) / max(steps, 1)
+        self.epsilon = MAX_EPSILON - per_step * self.num_step if self.num_step < steps else MIN_EPSILON
+
+    def select_actions(self, node, edge, in_mask):
+        """[E, N] int32 channel per link (epsilon-greedy per environment, first maximiser on ties: :342-344)."""
+        self._update_epsilon()
+        E, N, dev = self.E, self.num_D2D, self.env.dev
+        q = self.brain.forward_device(node, edge, in_mask=in_mask)
+        greedy = torch.argmax(q, dim=2).to(torch.int32)
+        explore = torch.rand((E, 1), generator=self.gen, device=dev) < self.epsilon
+        rnd = torch.randint(0, self.num_CH, (E, N), generator=self.gen, device=dev, dtype=torch.int32)
+        return torch.where(explore, rnd, greedy)
+
+    def generate_transitions(self, num_transitions):
+        """num_transitions steps of every environment into the replay ring (:409-553); returns rewards [T, E] (device)."""
+        rewards = []
+        for _ in range(num_transitions):
+            node, edge, im, om = self.env.pack_state()
+            actions = self.select_actions(node, edge, im)
+            _, _, _, reward = self.env.act(actions, self.v2v_weight, self.v2i_weight)       # :366-376, :513-519
+            self.num_step += 1
+            node_, edge_, _, _ = self.env.pack_state()                                       # the adjacency of s is re-used (:545, :583)
+            self.memory.add_device(node, edge, im, om, actions, reward, node_, edge_)
+            rewards.append(reward)
+        return torch.stack(rewards)
+
+    def replay(self):
+        """One replay step (:555-748), identical to ``Agent.replay`` but with device-side index sampling."""
+        B, N, CH = self.batch_size, self.num_D2D, self.num_CH
+        m = self.memory
+        if m.size >= B:
+            idx = torch.randperm(m.size, generator=self.gen, device=m.device)[:B]           # without replacement (:258-270)
+        else:
+            idx = torch.randint(0, m.size, (B,), generator=self.gen, device=m.device)
+        g = lambda t: t.index_select(0, idx)
+        node, edge, node_, edge_ = g(m.node), g(m.edge), g(m.node_), g(m.edge_)
+        im, om, action, reward = g(m.in_mask), g(m.out_mask), g(m.action), g(m.reward)
+        brain = self.brain
+        p = brain.forward_device(node, edge, in_mask=im)                                    # :664
+        p_ = brain.forward_device(node_, edge_, in_mask=im, target=True)                    # :665
+        y = torch.empty_like(p)
+        _lib.check(self._lib.v2v_td_target(ptr(p), ptr(p_), ptr(action), ptr(reward), float(self.gamma), ptr(y), B, N, CH,
+                                           _lib.current_stream()))                          # :668-692
+        losses = brain.train_step_device(node, edge, im, om, None, y)                       # :728
+        return losses, y.mean(dim=(0, 2)), p.mean(dim=(0, 2))
+
+    def train(self, num_episodes, num_train_steps, num_transition=50):
+        """Agent.train (:750-910) for E environments in lock step.  Returns (loss [episodes, steps, N], mean reward per
+        environment step [episodes, steps]) as host arrays."""
+        self.total_steps = num_episodes * num_train_steps * num_transition
+        self.num_step = 0
+        N = self.num_D2D
+        loss = np.zeros((num_episodes, num_train_steps, N))
+        rew = np.zeros((num_episodes, num_train_steps))
+        for ep in range(num_episodes):
+            self.env.new_random_game()                                                      # :810
+            for it in range(num_train_steps):
+                r = self.generate_transitions(num_transition)                               # :827
+                l, _, _ = self.replay()                                                     # :832
+                if self.num_step % UPDATE_TARGET_FREQUENCY < num_transition:                # :846-847 (steps advance by num_transition)
+                    self.brain.update_target_model()
+                loss[ep, it] = l.cpu().numpy()
+                rew[ep, it] = float(r.mean())
+        return loss, rew

@@ -122,3 +122,27 @@ def test_full_size_properties_and_brain_step(v2v):
                                      v2v._lib.current_stream()))
     hl = brain.train_step_device(node, edge, im, om, None, y)
     assert torch.isfinite(hl).all()
+
+
+def test_batched_dqn_loop_on_device(v2v):
+    """E environments x the reference DQN loop, nothing leaves the device but the per-step statistics."""
+    class Cfg:                                   # Sim_Config.RL_Config fields the agent reads (Sim_Config.py:8-24)
+        Batch_Size, Gamma, v2v_weight, v2i_weight = 256, 0.5, 1.0, 0.1
+    E, N = 128, 4
+    env = v2v.BatchedEnviron(E, n_veh=N, n_rb=4, seed=5)
+    agent = v2v.BatchedAgent(env, Cfg, memory_capacity=8192, seed=7, stages=3, per_slot=True)     # the reference's brain: per-slot weights
+    loss, rew = agent.train(num_episodes=2, num_train_steps=6, num_transition=4)
+    assert np.isfinite(loss).all() and np.isfinite(rew).all() and (rew > 0).all()
+    assert len(agent.memory) == min(8192, 2 * 6 * 4 * E) and agent.num_step == 48
+    assert agent.epsilon < 1.0 and agent.brain.iterations == 12
+    # replaying a fixed ring reduces the TD loss
+    first = float(agent.replay()[0].sum())
+    for _ in range(60):
+        last = float(agent.replay()[0].sum())
+    assert last < first
+    # actions are valid channels, greedy part uses the first maximiser
+    node, edge, im, om = env.pack_state()
+    agent.epsilon, agent.total_steps, agent.num_step = 0.0, 1, 10
+    a = agent.select_actions(node, edge, im)
+    q = agent.brain.forward_device(node, edge, in_mask=im)
+    assert torch.equal(a, torch.argmax(q, dim=2).to(torch.int32)) and int(a.min()) >= 0 and int(a.max()) < 4
