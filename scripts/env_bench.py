@@ -98,6 +98,23 @@ if __name__ == "__main__":
         us, us_ch, by, us_rng = gpu_point(E, N)
         gbs = by / (us_ch * 1e-6) / 1e9
         print(f"{E:6d} {N:3d} {us:15.1f} {E / (us * 1e-6):14.3e} {E / (us_rng * 1e-6):14.3e} {us_ch:12.1f} {gbs:8.1f} {gbs / PEAK['hbm_gbs']:6.3f}", flush=True)
+    # the whole DQN loop on the device: E environments act epsilon-greedily on the brain's Q, transitions go to the replay
+    # ring, one replay step (2 forwards + TD target + fwd/bwd/Adam on `batch` sampled transitions) per 4 environment steps
+    class Cfg:
+        Batch_Size, Gamma, v2v_weight, v2i_weight = 1024, 0.5, 1.0, 0.1
+    for E, N, kw in ((1024, 4, dict(stages=3, per_slot=True)), (1024, 20, dict(stages=2, per_slot=False)), (8192, 20, dict(stages=2, per_slot=False))):
+        env = v2v.BatchedEnviron(E, n_veh=N, n_rb=4, seed=3)
+        agent = v2v.BatchedAgent(env, Cfg, memory_capacity=1 << 16, seed=4, **kw)
+        env.new_random_game()
+        agent.total_steps = 10 ** 6
+        for _ in range(3):
+            agent.generate_transitions(4); agent.replay()
+        torch.cuda.synchronize(); t0 = time.perf_counter(); reps = 20
+        for _ in range(reps):
+            agent.generate_transitions(4); agent.replay()
+        torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / reps
+        print(f"# DQN loop on the device, E={E} N={N} {kw}: {dt * 1e3:.2f} ms per (4 env steps of all E + 1 replay step of {Cfg.Batch_Size}) = "
+              f"{4 * E / dt:.3e} transitions/s with learning", flush=True)
     for E, N in ((256, 4), (64, 20)):
         s = cpu_point(E, N)
         print(f"# CPU restatement (oracle/env_oracle.py, numpy fp64, vectorised over E={E}, mobility in Python loops), N={N}: "
