@@ -219,7 +219,8 @@ __device__ __forceinline__ void wgrad_block(const FusedOp& op, const float* aren
 
 __device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* arena, const float* Ws, const int* tab, int RP,
                                           int zero_row, int tid, const int (&my_blk)[kFusedBlkPerThread],
-                                          float (&wacc)[kFusedBlkPerThread][16], int my_bias, float& bacc, float* dWs) {
+                                          float (&wacc)[kFusedBlkPerThread][16], int my_bias, float& bacc, float* dWs,
+                                          int* dx_ctr) {
   // ---- weight gradient.  Large layers: 4x4 blocks owned by fixed threads, accumulated in registers across
   // tiles.  Small layers (op.nwt = RS > 0): every block is split over RS adjacent lanes by row groups, reduced
   // with shuffles, and the first lane adds the block into the CTA's shared accumulator (one owner per
@@ -271,12 +272,13 @@ __device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* 
   if (op.n_dx > 0) {
     const int row_groups = RP / 4;
     const int items = row_groups * (op.n_dx / 4);
-    // hand the items to the threads that had no weight-gradient work in this phase (cyclic owner range)
-    int rank = (tid - owners_begin - owners_n) % kFusedThreads;      // owner range may wrap around the CTA
-    if (rank < 0) rank += kFusedThreads;
-    int workers = kFusedThreads - owners_n;
-    if (workers < 96) { rank = kFusedThreads - 1 - tid; workers = kFusedThreads; }
-    for (int item = (rank < workers ? rank : items); item < items; item += workers) {
+    // Work queue: the threads without weight-gradient work start on the items at once, the block owners join as they
+    // finish (static splits left the two groups 20-40 % apart: profiles trace of bwd mlp2 / mlp1).  Every item writes
+    // its own outputs, so the result does not depend on who takes which item.
+    (void)owners_begin; (void)owners_n;
+    for (;;) {
+      const int item = atomicAdd(dx_ctr, 1);
+      if (item >= items) break;
       const int kg = item / row_groups, rg = item - kg * row_groups;
       const int r0 = rg * 4;
       const float* wr[4];
@@ -340,7 +342,9 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
                    const uint32_t* __restrict__ out_mask, const float* __restrict__ y, float* __restrict__ q_out, float* __restrict__ partial, float* __restrict__ head_loss, int B,
                    float inv_cnt) {
   extern __shared__ __align__(16) float smem[];
+  __shared__ int dx_ctr[2];                            // data-gradient work queues of two consecutive backward phases
   const int tid = threadIdx.x;
+  if (tid < 2) dx_ctr[tid] = 0;
   const int N = P->N, TG = P->TG, RP = P->RP, CH = P->CH, Dn = P->Dn, De = P->De;
   const int n_params = P->n_params, n_ops = P->n_ops, n_tab = P->n_tab, train = P->train;
   const int np_pad = (n_params + 3) & ~3;
@@ -422,6 +426,7 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
     if (trace) trace[warp * 2 + 1] = clock64();
     for (int oi = 0; oi < n_ops; ++oi) {
       const FusedOp& op = ops[oi];
+      if (tid == 0) dx_ctr[(oi + 1) & 1] = 0;              // the NEXT phase's work queue (idle: its last user ended a barrier ago)
       switch (op.type) {
         case FOP_GEMM: {
           const int rg4 = RP / 4;
@@ -432,7 +437,7 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
         }
         case FOP_AGG: agg_phase<NMAX>(op, arena, tab, mask_s, RP, N, TG, tid); break;
         case FOP_LOSS: loss_phase(P, arena, tab, hl_s, RP, valid_rows, inv_cnt, tid); break;
-        case FOP_BWD: bwd_phase(op, oi, arena, Ws, tab, RP, P->zero_row, tid, my_blk, wacc, my_bias, bacc, dWs); break;
+        case FOP_BWD: bwd_phase(op, oi, arena, Ws, tab, RP, P->zero_row, tid, my_blk, wacc, my_bias, bacc, dWs, &dx_ctr[oi & 1]); break;
         default: break;
       }
       if (trace) trace[((oi + 1) * kFusedWarps + warp) * 2] = clock64();
