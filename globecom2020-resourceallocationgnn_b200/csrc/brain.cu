@@ -319,6 +319,39 @@ extern "C" int v2v_brain_fused_info(v2v_brain* b, int B, int train, int* info8) 
   return rc;
 }
 
+// Host-only planning query of the tensor-core forward (no device needed).  info8 = {capable, graphs per tile, layers,
+// shared-memory bytes, operand planes per tile slot, floats of the staged weight image, tensor-memory columns used per
+// slot, tcgen05.mma instructions per tile}.
+extern "C" int v2v_tc_plan(const v2v_brain_config* cfg, int* info8) {
+  V2V_REQUIRE(cfg && info8, "v2v_tc_plan: bad argument");
+  for (int i = 0; i < 8; ++i) info8[i] = 0;
+  if (cfg->per_slot || cfg->num_d2d > 32 || cfg->num_d2d < 1 || cfg->stages < 1 || cfg->stages > 8) return 0;
+  std::vector<size_t> lw, lb;
+  size_t off = 0;
+  auto add_layer = [&](int K, int O) { lw.push_back(off); off += (size_t)K * O; lb.push_back(off); off += O; };
+  for (int s = 0; s < cfg->stages; ++s) add_layer((s == 0 ? cfg->node_dim : cfg->feedback + cfg->node_dim) + cfg->edge_dim + cfg->feedback, cfg->feedback);
+  int k = cfg->node_dim + 2 * cfg->feedback;
+  for (int i = 0; i < 3; ++i) { add_layer(k, cfg->hidden[i]); k = cfg->hidden[i]; }
+  add_layer(k, cfg->num_ch);
+  TcShape ts;
+  ts.N = cfg->num_d2d; ts.Dn = cfg->node_dim; ts.De = cfg->edge_dim; ts.F = cfg->feedback; ts.CH = cfg->num_ch; ts.S = cfg->stages;
+  ts.H1 = cfg->hidden[0]; ts.H2 = cfg->hidden[1]; ts.H3 = cfg->hidden[2];
+  ts.w_off = lw.data(); ts.b_off = lb.data();
+  TcPlan* p = new TcPlan();
+  if (tc_build_plan(ts, p) == 0) {
+    int cols = 0, mmas = 0;
+    for (int l = 0; l < p->n_layers; ++l) {
+      cols = std::max(cols, p->layers[l].dcol + 2 * p->layers[l].Npad);
+      mmas += 2 * (p->layers[l].Kpad / 8);
+    }
+    info8[0] = 1; info8[1] = p->TG; info8[2] = p->n_layers; info8[3] = p->smem_bytes; info8[4] = p->stage_planes;
+    info8[5] = p->w_floats + p->bias_floats; info8[6] = cols; info8[7] = mmas;
+  }
+  last_error().clear();
+  delete p;
+  return 0;
+}
+
 // Host-only planning query (no device needed): the fused program a brain of this configuration would
 // run for a batch of B graphs.  info8 as in v2v_brain_fused_info.
 extern "C" int v2v_fused_plan(const v2v_brain_config* cfg, int B, int train, int* info8) {

@@ -177,6 +177,9 @@ int v2v_brain_fused_info(v2v_brain* b, int B, int train, int* info8);
  * info4 = {capable, mode, graphs per tile, shared-memory bytes}.  Environment override at creation: V2V_TENSOR_CORE. */
 int v2v_brain_set_tensor_core(v2v_brain* b, int mode);
 int v2v_brain_tensor_core_info(const v2v_brain* b, int* info4);
+/* Host-only query (no device): info8 = {capable, graphs per tile, layers, shared-memory bytes, operand planes per tile
+ * slot, floats of the staged weight image, tensor-memory columns used per slot, tcgen05.mma instructions per tile}. */
+int v2v_tc_plan(const v2v_brain_config* cfg, int* info8);
 /* debugging aid: tensor-core forward that also dumps the raw fp32 accumulator [128][Npad] of `layer` for the first tile */
 int v2v_brain_tc_debug(v2v_brain* b, const float* node_dev, const float* edge_dev, const uint32_t* in_mask_dev, int B,
                        int layer, float* q_dev, float* dbg_dev, int* npad_out, void* stream);

@@ -65,3 +65,31 @@ def test_data_parallel_gradient_rule_gloo_world2(tmp_path):
     mp.spawn(_dp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert float(np.load(tmp_path / f"err{r}.npy")) < 1e-12
+
+
+def _cfg(v2v, N, S=2, per_slot=0, hidden=(80, 40, 20), F=16):
+    c = v2v._lib.BrainConfig()
+    c.num_d2d, c.node_dim, c.edge_dim, c.feedback, c.num_ch, c.stages, c.per_slot = N, 9, 4, F, 4, S, per_slot
+    c.hidden[0], c.hidden[1], c.hidden[2] = hidden
+    c.max_batch, c.dtype = 64, 0
+    c.lr, c.beta1, c.beta2, c.eps = 1e-3, 0.5, 0.999, 1e-7
+    return c
+
+
+def test_tensor_core_plan_host_query(v2v):
+    """The tcgen05 forward's plan (csrc/tc_forward.cu) is host logic: tile size, shared memory, tensor-memory columns and the
+    MMA count per tile follow from the brain's dimensions."""
+    import ctypes as C
+    lib = v2v.load_library()
+    info = (C.c_int32 * 8)()
+    for N, S in ((20, 2), (4, 3), (32, 1), (7, 2)):
+        assert lib.v2v_tc_plan(C.byref(_cfg(v2v, N, S)), info) == 0
+        capable, tg, layers, smem, planes, wimg, cols, mmas = list(info)
+        assert capable == 1 and tg == 128 // N and layers == S + 4
+        assert smem <= 227 * 1024 and planes == 12 and cols <= 256            # two slots share the 512 TMEM columns
+        # per tile: stage 0 contracts 16 (2 k-steps), later stages and the first MLP layer 48 (6), then 80, 48, 32: two MMAs each
+        assert mmas == 2 * (2 + 6 * (S - 1) + 6 + 10 + 6 + 4)
+        assert wimg == 2 * (16 * 16 + (S - 1) * 48 * 16 + 48 * 80 + 80 * 48 + 48 * 32 + 32 * 16) + 64 * -(-(16 * S + 80 + 48 + 32 + 16) // 64)
+    # outside the path: per-slot weights (the reference default), N > 32, layers wider than the tensor-memory regions
+    for cfg in (_cfg(v2v, 4, 3, per_slot=1), _cfg(v2v, 40), _cfg(v2v, 20, hidden=(200, 40, 20)), _cfg(v2v, 20, F=12)):
+        assert lib.v2v_tc_plan(C.byref(cfg), info) == 0 and info[0] == 0
