@@ -96,7 +96,6 @@ def mobility_case(seed):
     rec = Recorder()
     env = SP.make_env(8, seed)
     rng = np.random.default_rng(seed)
-    lanes = dict(u=(Environment.__dict__, ), )
     up, down, left, right = env.up_lanes, env.down_lanes, env.left_lanes, env.right_lanes
     starts = []
     for lane in left + right:
