@@ -165,3 +165,32 @@ def test_golden_env_states_follow_reference_rules():
     assert np.all(z["node"][:, :, 8] == 10.0)             # fixed V2V power 10 dBm (Environment.py:194-195)
     assert np.all(z["adj"].sum(1) == 2)                   # in-degree N-2
     assert np.all(np.diagonal(z["adj"], axis1=1, axis2=2) == 0)
+
+
+def test_huber_and_adam_against_independent_torch_implementations():
+    """Cross-checks against code that was not written for this repo (torch's Huber loss and Adam): the oracle's Huber
+    element/mean reduction is torch.nn.functional.huber_loss, and its Keras-Adam rule coincides with torch.optim.Adam when
+    eps -> 0 (the two differ only in where eps enters: Keras 2.2.4 adds it to sqrt(v) AFTER folding the bias corrections
+    into lr_t, BS_brain.py:212)."""
+    import torch
+    rng = np.random.default_rng(11)
+    q, y = rng.normal(0, 2, (32, 5, 4)), rng.normal(0, 2, (32, 5, 4))
+    total, per_head = O.brain_loss(q, y)
+    ref = [float(torch.nn.functional.huber_loss(torch.from_numpy(q[:, k]), torch.from_numpy(y[:, k]), delta=1.0, reduction="mean"))
+           for k in range(5)]
+    np.testing.assert_allclose(per_head, ref, rtol=1e-12)
+    assert abs(total - sum(ref)) <= 1e-12 * abs(total)
+    # Adam: 6 steps on a random quadratic, eps = 1e-30 in both rules, fp64
+    p0 = rng.normal(size=50)
+    pt = torch.tensor(p0.copy(), dtype=torch.float64, requires_grad=True)
+    b1, b2, lr = float(np.float32(0.5)), float(np.float32(0.999)), float(np.float32(1e-3))
+    opt = torch.optim.Adam([pt], lr=lr, betas=(b1, b2), eps=1e-30)
+    p, m, v = p0.copy(), np.zeros(50), np.zeros(50)
+    A = rng.normal(size=(50, 50)); A = A @ A.T / 50 + np.eye(50)
+    for t in range(1, 7):
+        g = A @ p
+        p, m, v = O.keras_adam_step(p, g, m, v, t, eps=1e-30)
+        opt.zero_grad()
+        (0.5 * pt @ torch.from_numpy(A) @ pt).backward()
+        opt.step()
+        np.testing.assert_allclose(p, pt.detach().numpy(), rtol=1e-9, atol=1e-12)
