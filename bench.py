@@ -464,6 +464,30 @@ def cpu_baseline_bounded(a):
             if k in ("value", "unit", "cores", "kind", "sample")}
 
 
+# --------------------------------------------------------------------------- batched-environment CPU leg
+def cpu_env_baseline(E, N, RB=4, budget_s=8.0):
+    """cpu_baseline leg of scripts/env_bench.py: seconds per step of E environments for the numpy restatement of the
+    simulator (oracle/env_oracle.py) on the host cores -- the oracle is only ever the thing compared against."""
+    from oracle import env_oracle as EO
+    rng = np.random.default_rng(0)
+    pos = rng.uniform(0, 700, (E, N, 2)); vel = rng.integers(10, 16, (E, N)).astype(float)
+    direction = rng.integers(0, 4, (E, N)); dest = (np.arange(N)[None] + rng.integers(1, N, (E, N))) % N
+    sv, si = rng.normal(0, 3, (E, N, N)), rng.normal(0, 8, (E, N))
+    _, _, v2v_ff, v2i_ff, _, v2i_abs = EO.renew_channels(pos, vel, sv, si, rng.normal(0, 3, (E, N, N)), rng.normal(0, 8, (E, N)),
+                                                         rng.normal(size=(E, N, N, RB, 2)), rng.normal(size=(E, N, RB, 2)))
+    actions = rng.integers(0, RB, (E, N))
+    t0 = time.perf_counter(); n = 0
+    while time.perf_counter() - t0 < budget_s:
+        EO.compute_reward(actions, dest, v2v_ff, v2i_ff, v2i_abs)
+        pos, direction = EO.renew_positions(pos, direction, vel, rng.random((E, N)))
+        sv, si, v2v_ff, v2i_ff, _, v2i_abs = EO.renew_channels(pos, vel, sv, si, rng.normal(0, 3, (E, N, N)), rng.normal(0, 8, (E, N)),
+                                                               rng.normal(size=(E, N, N, RB, 2)), rng.normal(size=(E, N, RB, 2)))
+        EO.pack_state(dest, v2v_ff, v2i_ff)
+        n += 1
+    return (time.perf_counter() - t0) / n
+
+
+
 def main():
     a = parse()
     if a.impl == "reference":

@@ -3,13 +3,13 @@ import os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import v2v_gnn_b200 as v2v
-from oracle import v2v_oracle as O
+from bench import synth_numpy
 N, F = 4, 16
 for per_slot in (True, False):
   for B in (1, 256, 512):
     brain = v2v.BS(N, 3, 1, 16, 1, 4, data_parallel=False, seed=1, per_slot=per_slot)
     rng = np.random.default_rng(0)
-    node, edge, adj, _ = O.synth_batch(B, N, rng)
+    node, edge, adj = (t.astype(np.float64) for t in synth_numpy(B, N, rng))
     A = np.stack([np.kron(a, np.eye(F)) for a in adj])
     x = {"Adjacency_Matrix": A}
     for k in range(N):

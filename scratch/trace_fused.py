@@ -1,12 +1,12 @@
 import sys, numpy as np, torch, ctypes as C
 sys.path.insert(0,'/root/repo')
 import v2v_gnn_b200 as v2v
-from oracle import v2v_oracle as O
+from bench import synth_numpy
 N,S,B=20,int(sys.argv[1]) if len(sys.argv)>1 else 2,int(sys.argv[2]) if len(sys.argv)>2 else 1024
 rng=np.random.default_rng(0)
 brain=v2v.BS(N,3,1,16,1,4,stages=S,per_slot=False,max_batch=B,data_parallel=False,seed=1)
 print(brain.fused_info(B,True))
-node,edge,adj,_=O.synth_batch(B,N,rng)
+node,edge,adj=synth_numpy(B,N,rng)
 nd,ed,ad=(torch.from_numpy(t.astype(np.float32)).cuda() for t in (node,edge,adj))
 im,om,_=v2v.pack_adjacency(ad)
 q=brain.forward_device(nd,ed,in_mask=im); y=q+1

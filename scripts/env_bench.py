@@ -14,8 +14,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from bench import load_peaks                                   # noqa: E402
-from oracle import env_oracle as EO                            # noqa: E402
+from bench import load_peaks, cpu_env_baseline                 # noqa: E402  (the CPU restatement is timed by bench.py's cpu_baseline leg)
 
 v2v = importlib.import_module("globecom2020-resourceallocationgnn_b200")
 PEAK = load_peaks()
@@ -70,25 +69,6 @@ def gpu_point(E, N, RB=4, reps=30):
     return us, us_ch, b * E, us_rng
 
 
-def cpu_point(E, N, RB=4, budget_s=8.0):
-    rng = np.random.default_rng(0)
-    pos = rng.uniform(0, 700, (E, N, 2)); vel = rng.integers(10, 16, (E, N)).astype(float)
-    direction = rng.integers(0, 4, (E, N)); dest = (np.arange(N)[None] + rng.integers(1, N, (E, N))) % N
-    sv, si = rng.normal(0, 3, (E, N, N)), rng.normal(0, 8, (E, N))
-    _, _, v2v_ff, v2i_ff, _, v2i_abs = EO.renew_channels(pos, vel, sv, si, rng.normal(0, 3, (E, N, N)), rng.normal(0, 8, (E, N)),
-                                                         rng.normal(size=(E, N, N, RB, 2)), rng.normal(size=(E, N, RB, 2)))
-    actions = rng.integers(0, RB, (E, N))
-    t0 = time.perf_counter(); n = 0
-    while time.perf_counter() - t0 < budget_s:
-        EO.compute_reward(actions, dest, v2v_ff, v2i_ff, v2i_abs)
-        pos, direction = EO.renew_positions(pos, direction, vel, rng.random((E, N)))
-        sv, si, v2v_ff, v2i_ff, _, v2i_abs = EO.renew_channels(pos, vel, sv, si, rng.normal(0, 3, (E, N, N)), rng.normal(0, 8, (E, N)),
-                                                               rng.normal(size=(E, N, N, RB, 2)), rng.normal(size=(E, N, RB, 2)))
-        EO.pack_state(dest, v2v_ff, v2i_ff)
-        n += 1
-    return (time.perf_counter() - t0) / n
-
-
 if __name__ == "__main__":
     print(f"# batched environment, one B200; HBM peak {PEAK['hbm_gbs']} GB/s ({PEAK['source']})")
     print(f"# step = reward + renew_positions + renew_channels_fastfading + pack_state; reference Environment.py measured in the")
@@ -116,6 +96,6 @@ if __name__ == "__main__":
         print(f"# DQN loop on the device, E={E} N={N} {kw}: {dt * 1e3:.2f} ms per (4 env steps of all E + 1 replay step of {Cfg.Batch_Size}) = "
               f"{4 * E / dt:.3e} transitions/s with learning", flush=True)
     for E, N in ((256, 4), (64, 20)):
-        s = cpu_point(E, N)
+        s = cpu_env_baseline(E, N)
         print(f"# CPU restatement (oracle/env_oracle.py, numpy fp64, vectorised over E={E}, mobility in Python loops), N={N}: "
               f"{s * 1e3:.1f} ms per step of all E = {E / s:.3e} env-steps/s on {os.cpu_count()} host cores")
