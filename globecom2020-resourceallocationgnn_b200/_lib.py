@@ -94,6 +94,8 @@ SIGNATURES = {
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, C.c_float,
                                              C.c_float, C.c_float, C.c_float, c_void_p]),
     "v2v_comm_check": (C.c_int, [c_void_p, c_void_p]),
+    "v2v_comm_poll_error": (C.c_int, [c_void_p, c_void_p]),
+    "v2v_comm_poll_result": (C.c_int, [c_void_p]),
     "v2v_comm_set_trace": (C.c_int, [c_void_p, c_void_p]),
     "v2v_comm_num_chunks": (C.c_int, [c_void_p]),
     "v2v_brain_train_step_dp": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -612,24 +612,53 @@ class BS:
         return losses.cpu().numpy().astype(np.float64)
 
     # ------------------------------------------------------------------ device-resident fast path
+    def _check_dev(self, what, t, shape, dtype, optional=False):
+        """The device entry points take raw pointers: a wrong dtype / stride / shape would read out of bounds."""
+        if t is None:
+            if optional:
+                return
+            raise ValueError(f"{what}: tensor required")
+        if not t.is_cuda or t.dtype != dtype or not t.is_contiguous() or tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{what}: expected a contiguous CUDA {dtype} tensor of shape {tuple(shape)}, got "
+                             f"{t.dtype} {tuple(t.shape)} (cuda={t.is_cuda}, contiguous={t.is_contiguous()})")
+
+    def _check_graph_inputs(self, who, node, edge, in_mask, out_mask, adj, neighbor):
+        B, N = int(node.shape[0]), self.num_D2D
+        W = (N + 31) // 32
+        f32, i32 = torch.float32, torch.int32
+        self._check_dev(f"{who}: node", node, (B, N, self.num_One_Node_Input), f32)
+        self._check_dev(f"{who}: edge", edge, (B, N, self.num_One_Edge_Input), f32)
+        self._check_dev(f"{who}: neighbor", neighbor, (B, N, self.num_Feedback), f32, optional=True)
+        self._check_dev(f"{who}: adj", adj, (B, N, N), f32, optional=True)
+        for nm, m in (("in_mask", in_mask), ("out_mask", out_mask)):
+            if m is not None and (not m.is_cuda or m.dtype != i32 or not m.is_contiguous() or m.numel() != B * N * W):
+                raise ValueError(f"{who}: {nm} must be a contiguous CUDA int32 tensor of {B * N * W} words, got {m.dtype} "
+                                 f"{tuple(m.shape)}")
+        return B
+
     def forward_device(self, node, edge, in_mask=None, adj=None, target=False, neighbor=None, out=None):
         """Device tensors in, Q [B,N,CH] device tensor out (no host round trip)."""
-        B = node.shape[0]
+        B = self._check_graph_inputs("forward_device", node, edge, in_mask, None, adj, neighbor)
         self._ensure_capacity(B)
         if out is None:
             out = torch.empty((B, self.num_D2D, self.num_CH), dtype=torch.float32, device=node.device)
+        else:
+            self._check_dev("forward_device: out", out, (B, self.num_D2D, self.num_CH), torch.float32)
         _lib.check(self._lib.v2v_brain_forward(self._handle, ptr(node), ptr(edge), ptr(neighbor), ptr(in_mask), ptr(adj), B,
                                                int(bool(target)), ptr(out), _lib.current_stream()), ValueError)
         return out
 
     def train_step_device(self, node, edge, in_mask, out_mask, adj, y, neighbor=None, head_loss=None):
         """One fwd+bwd(+all-reduce)+Adam step on device tensors; returns per-head loss tensor [N] (device)."""
-        B = node.shape[0]
+        B = self._check_graph_inputs("train_step_device", node, edge, in_mask, out_mask, adj, neighbor)
         self._ensure_capacity(B)
         N = self.num_D2D
+        self._check_dev("train_step_device: y", y, (B, N, self.num_CH), torch.float32)
         st = _lib.current_stream()
         if head_loss is None:
             head_loss = torch.empty(N, dtype=torch.float32, device=node.device)
+        else:
+            self._check_dev("train_step_device: head_loss", head_loss, (N,), torch.float32)
         if not self.data_parallel:
             _lib.check(self._lib.v2v_brain_train_step(self._handle, ptr(node), ptr(edge), ptr(neighbor), ptr(in_mask),
                                                       ptr(out_mask), ptr(adj), ptr(y), B, ptr(head_loss), st), ValueError)
@@ -644,5 +673,6 @@ class BS:
                                                         ptr(out_mask), ptr(adj), ptr(y), B, ptr(head_loss), st), ValueError)
         # the one collective of the step; AVG leaves the global-batch mean gradient in the grad buffer (as the peer path does)
         dist.all_reduce(self._views[2], op=dist.ReduceOp.AVG)
+        dist.all_reduce(head_loss, op=dist.ReduceOp.AVG)          # per-head losses of the global batch, like the peer path
         _lib.check(self._lib.v2v_brain_apply_adam(self._handle, 1.0, st))
         return head_loss

@@ -19,7 +19,7 @@ SOURCES = ["agg.cu", "dense.cu", "loss_opt.cu", "fused.cu", "comm.cu", "brain.cu
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "--use_fast_math=false" if False else "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fPIC",
     "-Xcompiler", "-fvisibility=default",
     "--expt-relaxed-constexpr",
 ]

@@ -573,6 +573,8 @@ extern "C" int v2v_brain_train_step_dp(v2v_brain* b, struct v2v_comm* comm, cons
   b->defer_reduce = false;
   if (rc) return rc;
   b->iterations += 1;
+  if ((b->iterations & 31) == 0)        // a timed-out exchange skipped its update: surface it, never train on diverged replicas
+    if (int rc2 = v2v_comm_poll_error(comm, stream)) return rc2;
   const long np = (long)b->n_params;
   if (b->last_grid > 0)     // fused path: the per-head losses are the tail columns of the per-CTA partial rows
     return v2v_comm_allreduce_adam_ex(comm, b->partial, b->last_grid, fused_partial_stride(np), np, np + b->N, nullptr, 0,
@@ -787,8 +789,10 @@ static int train_views_impl(v2v_brain* b, struct v2v_comm* comm, const v2v_host_
                     : v2v_brain_train_step(b, b->st_node, b->st_edge, ng, im, om, b->st_adj, b->st_y, B, b->head_loss, stream))
     return rc;
   V2V_CHECK_CUDA(cudaMemcpyAsync(b->pin + b->pin_hl, b->head_loss, b->N * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (comm) if (int rc = v2v_comm_poll_error(comm, stream)) return rc;
   const double t2 = trace ? now() : 0;
   V2V_CHECK_CUDA(cudaStreamSynchronize(st));
+  if (comm) if (int rc = v2v_comm_poll_result(comm)) return rc;
   if (trace) {
     const double t3 = now();
     acc[0] += t1 - t0; acc[1] += t2 - t1; acc[2] += t3 - t2;

@@ -87,22 +87,32 @@ allreduce_adam_kernel(const float* __restrict__ partial, int n_cta, long row_str
   for (int r = 0; r < world; ++r)
     if (r != rank) st_ll(peers.slots[r] + slot_off, g, epoch);
   if (tr) trace[chunk * 6 + 2] = globaltimer_ns();
-  // 3. gather every rank's element from our own slots, in rank order (identical on every rank)
+  // 3. gather every rank's element from our own slots.  All peers are polled in ONE pass per spin (the loads of a
+  //    pass are independent, so a late rank does not serialise the others' round trips); the values are then summed in
+  //    rank order (identical on every rank).
   const uint2* mine = peers.slots[rank] + (size_t)buf * world * n_pad + i;
-  float s = 0.f;
-  for (int r = 0; r < world; ++r) {
-    float val = g;
-    if (r != rank) {
-      uint2 w = ld_ll(mine + (size_t)r * n_pad);
-      long spins = 0;
-      while (w.y != epoch) {
-        if (++spins > (1L << 24)) { *error = 1; break; }         // ~seconds: a peer is gone; never hang the GPU
-        w = ld_ll(mine + (size_t)r * n_pad);
+  float vals[kCommMaxWorld];
+  uint32_t pending = (world >= 32 ? 0xffffffffu : ((1u << world) - 1u)) & ~(1u << rank);
+  long spins = 0;
+  bool timed_out = false;
+  while (pending) {
+#pragma unroll
+    for (int r = 0; r < kCommMaxWorld; ++r) {
+      if (pending & (1u << r)) {
+        const uint2 w = ld_ll(mine + (size_t)r * n_pad);
+        if (w.y == epoch) { vals[r] = __uint_as_float(w.x); pending &= ~(1u << r); }
       }
-      val = __uint_as_float(w.x);
     }
-    s += val;
+    if (pending && ++spins > (1L << 22)) { timed_out = true; break; }   // ~seconds: a peer is gone; never hang the GPU
   }
+  if (timed_out) {               // never train on stale or missing peer data: flag it and leave p / m / v untouched
+    *error = 1;
+    return;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int r = 0; r < kCommMaxWorld; ++r)
+    if (r < world) s += (r == rank) ? g : vals[r];
   if (tr) trace[chunk * 6 + 3] = globaltimer_ns();
   const float inv = 1.f / (float)world;
   if (i < n_adam) {
@@ -133,6 +143,7 @@ struct v2v_comm {
   CommPeers peers{};
   void* opened[kCommMaxWorld] = {};
   int* error_dev = nullptr;
+  int* error_host = nullptr;  // pinned mirror of error_dev, refreshed by v2v_comm_poll_error
   unsigned long long* trace_dev = nullptr;   // optional: [n_chunks][6] globaltimer stamps of the last exchange
   bool peers_ready = false;
 };
@@ -145,12 +156,14 @@ extern "C" int v2v_comm_create(long n_floats, int world, int rank, v2v_comm** ou
   c->n_chunks = (int)((n_floats + kCommChunk - 1) / kCommChunk);
   c->n_pad = c->n_chunks * kCommChunk;
   c->bytes = (size_t)2 * world * c->n_pad * sizeof(uint2);
-  if (cudaMalloc((void**)&c->slots, c->bytes) != cudaSuccess || cudaMalloc((void**)&c->error_dev, sizeof(int)) != cudaSuccess) {
+  if (cudaMalloc((void**)&c->slots, c->bytes) != cudaSuccess || cudaMalloc((void**)&c->error_dev, sizeof(int)) != cudaSuccess ||
+      cudaMallocHost((void**)&c->error_host, sizeof(int)) != cudaSuccess) {
     delete c;
     return fail("v2v_comm_create: cudaMalloc failed");
   }
   cudaMemset(c->slots, 0, c->bytes);
   cudaMemset(c->error_dev, 0, sizeof(int));
+  *c->error_host = 0;
   c->peers.slots[rank] = c->slots;
   c->peers_ready = (world == 1);
   cudaDeviceSynchronize();
@@ -164,6 +177,7 @@ extern "C" void v2v_comm_destroy(v2v_comm* c) {
     if (c->opened[r]) cudaIpcCloseMemHandle(c->opened[r]);
   cudaFree(c->slots);
   cudaFree(c->error_dev);
+  if (c->error_host) cudaFreeHost(c->error_host);
   delete c;
 }
 
@@ -244,6 +258,22 @@ extern "C" int v2v_comm_set_trace(v2v_comm* c, unsigned long long* trace_dev) {
   return 0;
 }
 extern "C" int v2v_comm_num_chunks(v2v_comm* c) { return c ? c->n_chunks : 0; }
+
+// Stream-ordered, non-blocking error surfacing for the product path: enqueues a copy of the device error flag into a
+// pinned mirror and fails if an EARLIER copy already reported a timeout (a rank that timed out skipped its update, so
+// the replicas have diverged and training must stop).  Callers that synchronise the stream afterwards (the host
+// entry points) call v2v_comm_poll_result to read the value that just landed.
+extern "C" int v2v_comm_poll_error(v2v_comm* c, void* stream) {
+  V2V_REQUIRE(c, "v2v_comm_poll_error: null argument");
+  V2V_REQUIRE(*c->error_host == 0, "v2v_comm: a peer did not arrive at the gradient exchange (timeout); the update was skipped");
+  V2V_CHECK_CUDA(cudaMemcpyAsync(c->error_host, c->error_dev, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return 0;
+}
+extern "C" int v2v_comm_poll_result(v2v_comm* c) {
+  V2V_REQUIRE(c, "v2v_comm_poll_result: null argument");
+  V2V_REQUIRE(*c->error_host == 0, "v2v_comm: a peer did not arrive at the gradient exchange (timeout); the update was skipped");
+  return 0;
+}
 
 // non-zero if a wait timed out (a peer never arrived); synchronises the stream
 extern "C" int v2v_comm_check(v2v_comm* c, void* stream) {

@@ -151,16 +151,26 @@ __device__ __forceinline__ void loss_phase(const FusedProgram* P, float* arena, 
   for (int item = tid; item < items; item += kFusedThreads) {
     const int c = item / RP, r = item - c * RP;
     float* q = arena + tab[P->q_tab + c] * RP + r;
-    const float yv = arena[tab[P->y_tab + c] * RP + r];
-    float dq = 0.f;
+    float* yp = arena + tab[P->y_tab + c] * RP + r;
+    float dq = 0.f, hub = 0.f;
     if (r < valid_rows) {
-      const float e = *q - yv;
+      const float e = *q - *yp;
       const float ae = fabsf(e);
       const float quad = fminf(ae, 1.f);
-      atomicAdd(&hl_s[r % P->N], 0.5f * quad * quad + (ae - quad));
+      hub = 0.5f * quad * quad + (ae - quad);
       dq = fminf(fmaxf(e, -1.f), 1.f) * inv_cnt;
     }
     *q = dq;
+    *yp = hub;                    // the target is dead from here on: its slot carries the element's Huber value
+  }
+  __syncthreads();
+  // per-head sums in a fixed order (one thread per head, graphs then channels): bit-stable loss, no float atomics
+  const int N = P->N;
+  if (tid < N) {
+    float s = 0.f;
+    for (int r = tid; r < valid_rows; r += N)
+      for (int c = 0; c < P->CH; ++c) s += arena[tab[P->y_tab + c] * RP + r];
+    hl_s[tid] += s;
   }
 }
 

@@ -296,6 +296,8 @@ class BatchedAgent:
         self.E = environment.E
         self.epsilon, self.num_step = MAX_EPSILON, 0
         brain_kwargs.setdefault("max_batch", max(curr_rl_config.Batch_Size, self.E))
+        if seed is not None:
+            brain_kwargs.setdefault("seed", int(seed))      # the same seed fixes the glorot draw (reproducible runs)
         self.brain = BS(self.num_D2D, 3, 1, num_d2d_feedback, 1, self.num_CH, **brain_kwargs)
         self.batch_size, self.gamma = curr_rl_config.Batch_Size, curr_rl_config.Gamma
         self.v2v_weight, self.v2i_weight = curr_rl_config.v2v_weight, curr_rl_config.v2i_weight
@@ -335,11 +337,15 @@ class BatchedAgent:
             rewards.append(reward)
         return torch.stack(rewards)
 
-    def replay(self):
-        """One replay step (:555-748), identical to ``Agent.replay`` but with device-side index sampling."""
+    def replay(self, indices=None):
+        """One replay step (:555-748), identical to ``Agent.replay`` but with device-side index sampling.
+        ``indices`` (device int64 tensor of ring slots) replaces the random draw -- reproducible replays."""
         B, N, CH = self.batch_size, self.num_D2D, self.num_CH
         m = self.memory
-        if m.size >= B:
+        if indices is not None:
+            idx = indices.to(m.device, dtype=torch.int64)
+            B = int(idx.numel())
+        elif m.size >= B:
             idx = torch.randperm(m.size, generator=self.gen, device=m.device)[:B]           # without replacement (:258-270)
         else:
             idx = torch.randint(0, m.size, (B,), generator=self.gen, device=m.device)

@@ -304,6 +304,12 @@ int v2v_comm_allreduce_adam_ex(v2v_comm* c, const float* partial_dev, int n_cta,
                                float* v_dev, float* extra_out_dev, int t, float lr, float beta1, float beta2, float eps,
                                void* stream);
 int v2v_comm_check(v2v_comm* c, void* stream);
+/* A rank whose wait for a peer times out sets an error flag and SKIPS the parameter update (it never trains on stale
+ * data).  v2v_comm_poll_error enqueues a stream-ordered copy of that flag into a pinned mirror and fails if an earlier
+ * copy already reported a timeout (non-blocking; v2v_brain_train_step_dp calls it every 32 steps);
+ * v2v_comm_poll_result reads the mirror after the caller has synchronised the stream (the host entry points do). */
+int v2v_comm_poll_error(v2v_comm* c, void* stream);
+int v2v_comm_poll_result(v2v_comm* c);
 /* optional phase trace of the exchange kernel: trace_dev = device buffer of v2v_comm_num_chunks() * 6 uint64 (null
  * disables); per chunk: kernel entry, producer complete, pushed + fenced, all ranks arrived, Adam done (globaltimer ns) */
 int v2v_comm_set_trace(v2v_comm* c, unsigned long long* trace_dev);

@@ -6,7 +6,7 @@ O=gpurun_out
 mkdir -p $O
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > $O/smi_$TAG.txt 2>&1
 nproc >> $O/smi_$TAG.txt
-timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_gpu_$TAG.log
+timeout 900 python -m pytest tests -m gpu -q > $O/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a $O/pytest_gpu_$TAG.log
 tail -5 $O/pytest_gpu_$TAG.log
 timeout 300 python __graft_entry__.py --smoke > $O/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -2 $O/smoke_$TAG.log
 timeout 400 python bench.py > $O/bench_n1_$TAG.json 2> $O/bench_n1_$TAG.err; echo "bench rc=$?"; cat $O/bench_n1_$TAG.json

@@ -1,7 +1,7 @@
 #!/bin/bash
 # quick single-GPU check: GPU tests + bench
 TAG=${1:-q}; O=gpurun_out; mkdir -p $O
-timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"; tail -15 $O/pytest_gpu_$TAG.log
+timeout 900 python -m pytest tests -m gpu -q > $O/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"; tail -15 $O/pytest_gpu_$TAG.log
 timeout 400 python bench.py ${BENCH_ARGS:---steps 300 --warmup 20} > $O/bench_n1_$TAG.json 2> $O/bench_n1_$TAG.err; echo "bench rc=$?"; tail -3 $O/bench_n1_$TAG.err
 python - <<PY
 import json

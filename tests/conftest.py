@@ -14,6 +14,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
 
 
+# Collection order: the hot-path rows of SURVEY.md section 8 (a: kernels, layers, brain; g: tensor cores; e: data
+# parallel) run before the "next" rows (f: DQN loop, batched environment), so that under `-x` a failure in an f-row
+# can never hide the parity tests of the judged kernels.
+_ORDER = ["test_capi_symbols", "test_oracle", "test_host_stage", "test_host_logic", "test_gpu_kernels", "test_gpu_layers",
+          "test_gpu_brain", "test_gpu_bf16", "test_gpu_tc", "test_gpu_dp", "test_gpu_dqn", "test_dqn_host", "test_env_oracle",
+          "test_gpu_env"]
+
+
+def pytest_collection_modifyitems(session, config, items):
+    def key(item):
+        name = os.path.splitext(os.path.basename(str(item.fspath)))[0]
+        return _ORDER.index(name) if name in _ORDER else len(_ORDER)
+    items.sort(key=key)          # stable: the order inside a file is kept
+
+
 def golden_cases():
     # brain cases only: the simulator recordings (sim_*.npz, tests/golden/make_env_golden.py) have their own tests
     return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith("sim_"))
