@@ -93,10 +93,13 @@ class BS:
       max_batch   capacity of the device workspace (grown on demand)
       data_parallel  all-reduce gradients over torch.distributed's default group
       seed        seed of the glorot_uniform initialisation
+      dtype       "f32" (reference arithmetic; default) or "bf16": bf16 contraction operands with fp32 accumulation on
+                  the tensor cores for forward AND backward (csrc/tc_train.cu; BASELINE configs[2]); fp32 master
+                  weights, gradients and Adam.  Shared weights, N <= 32, <= 3 stages, binary adjacency only.
     """
 
     def __init__(self, num_d2d, input_node_info, input_edge_info, num_d2d_feedback, num_d2d_neighbor, num_ch,
-                 stages=3, per_slot=True, hidden=(80, 40, 20), max_batch=1024, data_parallel=None, seed=None):
+                 stages=3, per_slot=True, hidden=(80, 40, 20), max_batch=1024, data_parallel=None, seed=None, dtype="f32"):
         self.num_D2D = int(num_d2d)
         self.num_Neighbor = int(num_d2d_neighbor)
         self.num_CH = int(num_ch)
@@ -110,6 +113,9 @@ class BS:
         self.stages = int(stages)
         self.per_slot = bool(per_slot)
         self.hidden = tuple(int(h) for h in hidden)
+        if str(dtype) not in ("f32", "fp32", "float32", "bf16", "bfloat16"):
+            raise ValueError(f"dtype must be 'f32' or 'bf16', got {dtype!r}")
+        self.dtype = "bf16" if str(dtype) in ("bf16", "bfloat16") else "f32"
         if len(self.hidden) != 3:
             raise ValueError("the decision MLP has three hidden layers (BS_brain.py:176-178)")
         self._lib = _lib.load()
@@ -136,7 +142,7 @@ class BS:
         cfg.num_d2d, cfg.node_dim, cfg.edge_dim = self.num_D2D, self.num_One_Node_Input, self.num_One_Edge_Input
         cfg.feedback, cfg.num_ch, cfg.stages, cfg.per_slot = self.num_Feedback, self.num_CH, self.stages, int(self.per_slot)
         cfg.hidden[0], cfg.hidden[1], cfg.hidden[2] = self.hidden
-        cfg.max_batch, cfg.dtype = max_batch, 0
+        cfg.max_batch, cfg.dtype = max_batch, (_lib.V2V_BF16 if self.dtype == "bf16" else _lib.V2V_F32)
         cfg.lr, cfg.beta1, cfg.beta2, cfg.eps = 1e-3, 0.5, 0.999, 1e-7           # :212, K.epsilon()
         h = C.c_void_p()
         _lib.check(self._lib.v2v_brain_create(C.byref(cfg), C.byref(h)), ValueError)

@@ -17,6 +17,7 @@
 #include "fused.cuh"
 #include "host_stage.cuh"
 #include "tc_forward.cuh"
+#include "tc_train.cuh"
 
 namespace v2v {
 
@@ -103,6 +104,11 @@ struct v2v_brain {
   TcPlan tc_plan;
   TcPlan* tc_plan_dev = nullptr;
   float* tc_wimg = nullptr;                     // staged weight image (hi/lo planes + biases) of the last call
+  // bf16 configuration (cfg.dtype == V2V_BF16): every contraction of forward AND backward on tcgen05 (tc_train.cu)
+  bool bf16 = false;
+  TtPlan* tt_plan = nullptr;                    // host copy
+  TtPlan* tt_plan_dev = nullptr;
+  void* tt_wimg = nullptr;                      // bf16 weight image + fp32 biases of the last call
 };
 
 static FusedShape fused_shape(const v2v_brain* b) {
@@ -173,6 +179,9 @@ extern "C" void v2v_brain_destroy(v2v_brain* b) {
   cudaFree(b->partial);
   cudaFree(b->tc_plan_dev);
   cudaFree(b->tc_wimg);
+  cudaFree(b->tt_plan_dev);
+  cudaFree(b->tt_wimg);
+  delete b->tt_plan;
   for (auto& kv : b->fused_cache) { cudaFree(kv.second->dev); delete kv.second; }
   delete b;
 }
@@ -183,7 +192,8 @@ extern "C" int v2v_brain_create(const v2v_brain_config* cfg, v2v_brain** out) {
   V2V_REQUIRE(cfg->node_dim > 0 && cfg->edge_dim > 0 && cfg->feedback > 0 && cfg->num_ch > 0, "v2v_brain_create: non-positive dimension");
   V2V_REQUIRE(cfg->stages >= 1 && cfg->stages <= 8, "v2v_brain_create: stages=%d out of range [1,8]", cfg->stages);
   V2V_REQUIRE(cfg->max_batch >= 1, "v2v_brain_create: max_batch must be >= 1");
-  V2V_REQUIRE(cfg->dtype == V2V_F32, "v2v_brain_create: only V2V_F32 activations are implemented in the brain");
+  V2V_REQUIRE(cfg->dtype == V2V_F32 || cfg->dtype == V2V_BF16, "v2v_brain_create: unknown dtype %d", cfg->dtype);
+  V2V_REQUIRE(cfg->dtype == V2V_F32 || !cfg->per_slot, "v2v_brain_create: the bf16 brain is the shared-weight one (per_slot = 0)");
   for (int i = 0; i < 3; ++i) V2V_REQUIRE(cfg->hidden[i] > 0, "v2v_brain_create: hidden[%d] must be > 0", i);
   v2v_brain* b = new v2v_brain();
   b->cfg = *cfg;
@@ -263,6 +273,33 @@ extern "C" int v2v_brain_create(const v2v_brain_config* cfg, v2v_brain** out) {
     }
     last_error().clear();
     if (const char* e = getenv("V2V_TENSOR_CORE")) b->tc_mode = atoi(e);
+  }
+  if (cfg->dtype == V2V_BF16) {
+    TtShape ts;
+    ts.N = b->N; ts.Dn = b->Dn; ts.De = b->De; ts.F = b->F; ts.CH = b->CH; ts.S = b->S;
+    ts.H1 = cfg->hidden[0]; ts.H2 = cfg->hidden[1]; ts.H3 = cfg->hidden[2];
+    ts.w_off = b->lw.data(); ts.b_off = b->lb.data(); ts.n_params = b->n_params;
+    b->tt_plan = new TtPlan();
+    int rc2 = tt_build_plan(ts, b->tt_plan);
+    if (rc2 == 0) {
+      const size_t img = (size_t)b->tt_plan->w_elems * 2 + (size_t)b->tt_plan->bias_floats * 4;
+      if (cudaMalloc((void**)&b->tt_plan_dev, sizeof(TtPlan)) != cudaSuccess ||
+          cudaMemcpy(b->tt_plan_dev, b->tt_plan, sizeof(TtPlan), cudaMemcpyHostToDevice) != cudaSuccess ||
+          cudaMalloc(&b->tt_wimg, img) != cudaSuccess)
+        rc2 = fail("v2v_brain_create: device allocation failed (bf16 plan)");
+    }
+    if (rc2 == 0 && !b->partial) {
+      b->partial_ctas = sm_count();
+      const size_t pbytes = (size_t)b->partial_ctas * tt_partial_stride((long)b->n_params) * sizeof(float);
+      if (cudaMalloc((void**)&b->partial, pbytes) != cudaSuccess) rc2 = fail("v2v_brain_create: device allocation failed (partials)");
+      else cudaMemset(b->partial, 0, pbytes);
+    }
+    if (rc2) {
+      std::string e = last_error();
+      v2v_brain_destroy(b);
+      return fail("%s", e.c_str());
+    }
+    b->bf16 = true;
   }
   cudaDeviceSynchronize();
   *out = b;
@@ -346,6 +383,34 @@ extern "C" int v2v_tc_plan(const v2v_brain_config* cfg, int* info8) {
     }
     info8[0] = 1; info8[1] = p->TG; info8[2] = p->n_layers; info8[3] = p->smem_bytes; info8[4] = p->stage_planes;
     info8[5] = p->w_floats + p->bias_floats; info8[6] = cols; info8[7] = mmas;
+  }
+  last_error().clear();
+  delete p;
+  return 0;
+}
+
+// Host-only planning query of the bf16 tensor-core training kernel (csrc/tc_train.cu).  info8 = {capable, graphs per
+// tile, steps per training tile, tcgen05.mma instructions per training tile, shared-memory bytes, operand planes
+// (activations + gradients), bf16 weight-image elements, weight-gradient column blocks}.
+extern "C" int v2v_tt_plan(const v2v_brain_config* cfg, int* info8) {
+  V2V_REQUIRE(cfg && info8, "v2v_tt_plan: bad argument");
+  for (int i = 0; i < 8; ++i) info8[i] = 0;
+  if (cfg->per_slot || cfg->num_d2d < 1) return 0;
+  std::vector<size_t> lw, lb;
+  size_t off = 0;
+  auto add_layer = [&](int K, int O) { lw.push_back(off); off += (size_t)K * O; lb.push_back(off); off += O; };
+  for (int s = 0; s < cfg->stages; ++s) add_layer((s == 0 ? cfg->node_dim : cfg->feedback + cfg->node_dim) + cfg->edge_dim + cfg->feedback, cfg->feedback);
+  int k = cfg->node_dim + 2 * cfg->feedback;
+  for (int i = 0; i < 3; ++i) { add_layer(k, cfg->hidden[i]); k = cfg->hidden[i]; }
+  add_layer(k, cfg->num_ch);
+  TtShape ts;
+  ts.N = cfg->num_d2d; ts.Dn = cfg->node_dim; ts.De = cfg->edge_dim; ts.F = cfg->feedback; ts.CH = cfg->num_ch; ts.S = cfg->stages;
+  ts.H1 = cfg->hidden[0]; ts.H2 = cfg->hidden[1]; ts.H3 = cfg->hidden[2];
+  ts.w_off = lw.data(); ts.b_off = lb.data(); ts.n_params = off;
+  TtPlan* p = new TtPlan();
+  if (tt_build_plan(ts, p) == 0) {
+    info8[0] = 1; info8[1] = p->TG; info8[2] = p->n_steps_train; info8[3] = p->n_mma; info8[4] = p->smem_bytes;
+    info8[5] = p->x_planes + p->dz_planes; info8[6] = p->w_elems; info8[7] = p->n_blocks;
   }
   last_error().clear();
   delete p;
@@ -444,6 +509,12 @@ extern "C" int v2v_brain_forward(v2v_brain* b, const float* node_dev, const floa
   if (B == 0) return 0;
   V2V_REQUIRE(node_dev && edge_dev && q_dev, "v2v_brain_forward: null pointer");
   V2V_REQUIRE(in_mask_dev || adj_dev, "v2v_brain_forward: need in_mask or adj");
+  if (b->bf16) {
+    V2V_REQUIRE(in_mask_dev && !neighbor_dev, "v2v_brain_forward: the bf16 brain needs the binary adjacency masks and the "
+                "reference's all-zero neighbour input");
+    return tt_launch(*b->tt_plan, b->tt_plan_dev, b->params[target ? 1 : 0], b->tt_wimg, node_dev, edge_dev, in_mask_dev, nullptr,
+                     nullptr, q_dev, nullptr, B, 0, (cudaStream_t)stream);
+  }
   if (b->tc_capable && b->tc_mode > 0 && b->fused_enabled && in_mask_dev && !neighbor_dev &&
       (b->tc_mode >= 2 || ceil_div(B, b->tc_plan.TG) >= 2 * sm_count()))
     return tc_forward_launch(b->tc_plan, b->tc_plan_dev, b->params[target ? 1 : 0], b->tc_wimg, node_dev, edge_dev, in_mask_dev,
@@ -474,6 +545,16 @@ extern "C" int v2v_brain_forward_backward(v2v_brain* b, const float* node, const
   float* Gd = b->params[2];
   float* hl = head_loss_dev ? head_loss_dev : b->head_loss;
 
+  if (b->bf16) {
+    V2V_REQUIRE(im && om && !neigh, "v2v_brain_forward_backward: the bf16 brain needs the binary adjacency masks and the "
+                "reference's all-zero neighbour input");
+    const int grid = tt_grid(*b->tt_plan, B);
+    b->last_grid = grid;
+    if (int rc = tt_launch(*b->tt_plan, b->tt_plan_dev, P, b->tt_wimg, node, edge, im, om, y, nullptr, b->partial, B, 1, st)) return rc;
+    if (b->defer_reduce) return 0;
+    return fused_reduce_adam(b->partial, grid, tt_partial_stride((long)b->n_params), Gd, nullptr, nullptr, nullptr,
+                             (long)b->n_params, N, hl, 0, 0.f, 0.f, 0.f, 0.f, 1.f, st);
+  }
   if (use_fused(b, im, neigh)) {
     v2v_brain::FusedEntry* e = nullptr;
     if (int rc = fused_get(b, B, 1, &e)) return rc;

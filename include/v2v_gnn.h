@@ -151,7 +151,7 @@ typedef struct v2v_brain_config {
   int per_slot;       /* 1: one weight set per node slot (reference, :121-200); 0: shared */
   int hidden[3];      /* decision MLP widths (reference 80,40,20, :176-178) */
   int max_batch;      /* workspace capacity in graphs                      */
-  int dtype;          /* V2V_F32 (V2V_BF16: activations stored bf16)       */
+  int dtype;          /* V2V_F32, or V2V_BF16: bf16 operands / fp32 accumulate on the tensor cores (see v2v_tt_plan) */
   float lr, beta1, beta2, eps;   /* Adam (:212): 1e-3, 0.5, 0.999, 1e-7    */
 } v2v_brain_config;
 
@@ -180,6 +180,12 @@ int v2v_brain_tensor_core_info(const v2v_brain* b, int* info4);
 /* Host-only query (no device): info8 = {capable, graphs per tile, layers, shared-memory bytes, operand planes per tile
  * slot, floats of the staged weight image, tensor-memory columns used per slot, tcgen05.mma instructions per tile}. */
 int v2v_tc_plan(const v2v_brain_config* cfg, int* info8);
+/* The bf16 configuration (dtype = V2V_BF16; BASELINE configs[2]): forward, Huber head and the whole backward run as ONE
+ * tcgen05 kernel (csrc/tc_train.cu) -- bf16 contraction operands, fp32 accumulation in tensor memory, fp32 bias / ReLU /
+ * aggregation / loss, fp32 master weights and Adam.  Shared weights, N <= 32, <= 3 stages, feedback width 16.
+ * Host-only query: info8 = {capable, graphs per tile, steps per training tile, tcgen05.mma per training tile,
+ * shared-memory bytes, operand planes, bf16 weight-image elements, weight-gradient column blocks}. */
+int v2v_tt_plan(const v2v_brain_config* cfg, int* info8);
 /* debugging aid: tensor-core forward that also dumps the raw fp32 accumulator [128][Npad] of `layer` for the first tile */
 int v2v_brain_tc_debug(v2v_brain* b, const float* node_dev, const float* edge_dev, const uint32_t* in_mask_dev, int B,
                        int layer, float* q_dev, float* dbg_dev, int* npad_out, void* stream);
