@@ -8,9 +8,10 @@
 Tolerances (|x - ref| / max |ref|).  Q vs (a): median <= 1e-6, at most 3 % of the elements beyond 1e-3 and none beyond
 2e-2 -- the device accumulates in fp32 (order unspecified) where the emulation accumulates in fp64, so a value that sits
 on a bf16 rounding boundary can flip by one bf16 ulp (2^-8 relative; the aggregated rows reach |a| ~ 2e3, ulp 16) and
-that flip propagates to ~1 % of the outputs; everything else agrees to ~1e-8.  Q vs (b): 3e-2.  Gradients vs (a) 5e-3,
-vs (b) 6e-2 with cosine similarity >= 0.995 on well-conditioned targets (a consistent TD-like shift; with pure-noise targets the gradient is a
-random-sign sum and bf16-vs-fp64 is ill-conditioned whatever the implementation: measured 0.3 for the emulation itself).
+that flip propagates to ~1 % of the outputs; everything else agrees to ~1e-8.  Q vs (b): 5e-2.  Gradients vs (a) 5e-3,
+vs (b) 0.15 with cosine similarity >= 0.99 on well-conditioned targets (a consistent TD-like shift; with pure-noise targets the gradient is a
+random-sign sum and bf16-vs-fp64 is ill-conditioned whatever the implementation: measured 0.3 for the emulation itself;
+the emulation's own distance to fp64 on these cases is 1-3e-2 for Q and 3-9e-2 for the gradients).
 """
 import numpy as np
 import pytest
@@ -21,7 +22,7 @@ from oracle import bf16_emul as E
 
 pytestmark = pytest.mark.gpu
 
-Q_EMUL_MAX, Q_F64, G_EMUL, G_F64 = 2e-2, 3e-2, 5e-3, 6e-2
+Q_EMUL_MAX, Q_F64, G_EMUL, G_F64 = 2e-2, 5e-2, 5e-3, 0.15
 
 
 def check_q_against_emulation(q, q_emul):
@@ -85,7 +86,7 @@ def test_bf16_train_step(v2v, N, S, B):
     assert rel(g, ge) <= G_EMUL, rel(g, ge)
     assert rel(g, go) <= G_F64, rel(g, go)
     cos = float(g @ go / (np.linalg.norm(g) * np.linalg.norm(go)))
-    assert cos >= 0.995, cos
+    assert cos >= 0.99, cos
     # dead parameters (stage-0 neighbour rows: the reference feeds zeros, BS_brain.py:478) have exactly zero gradient
     g_layers = O.unflatten_params(d, g)
     assert np.all(g_layers[0]["W"][0, d.Dn + d.De:] == 0.0)
