@@ -56,6 +56,7 @@ def parse():
     ap.add_argument("--dtype", default=None, choices=["f32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the aggregation roofline point (profiling runs)")
     a = ap.parse_args()
     if a.config == "c3":                              # BASELINE configs[2]
         a.stages = 3
@@ -256,8 +257,9 @@ def run_engine_arm(a):
     roof = predict = cpu = None
     clocks = ClockSampler(local)
     if rank == 0:
-        roof = agg_roofline(v2v, lib, dev, a.agg_batch, N, a.sparse, clocks)
-        if world == 1:
+        if not a.no_roofline:
+            roof = agg_roofline(v2v, lib, dev, a.agg_batch, N, a.sparse, clocks)
+        if world == 1 and not a.no_roofline:
             if a.dtype == "f32":
                 predict = predict_point(v2v, dev, a.agg_batch, N, S, a.sparse)
             if not a.no_cpu_baseline:

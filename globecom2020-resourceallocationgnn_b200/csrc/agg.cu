@@ -120,24 +120,15 @@ static int agg_block_min_n() {      // tunable for experiments: V2V_AGG_BLOCK_MI
   return v;
 }
 
-static int agg_walk_mode() {        // V2V_AGG_WALK=0 restores the dense predicated form for 8 < N <= 20 (experiments)
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("V2V_AGG_WALK");
-    v = e ? atoi(e) : 1;
-  }
-  return v;
-}
-
-template <typename T, int MT, int MP, int NC = 0, bool WALK = false>
+template <typename T, int MT, int MP, int NC = 0>
 static int launch_fast(const T* H, const uint32_t* mask, const T* addend, T* out, int B, int N, bool independent,
                        cudaStream_t st) {
   constexpr int TG = 32 / (4 * MP);
   AggLaunchCfg cfg;
   cfg.dep_wait = !independent;
   cfg.ctas_per_sm = agg_fast_fits<T>(N, TG, addend != nullptr, kAggWarps, 2) ? 2 : 1;
-  if (addend) return launch_agg_fast<T, MT, MP, true, kAggWarps, true, NC, WALK>(H, mask, addend, out, B, N, cfg, st);
-  return launch_agg_fast<T, MT, MP, false, kAggWarps, true, NC, WALK>(H, mask, addend, out, B, N, cfg, st);
+  if (addend) return launch_agg_fast<T, MT, MP, true, kAggWarps, true, NC>(H, mask, addend, out, B, N, cfg, st);
+  return launch_agg_fast<T, MT, MP, false, kAggWarps, true, NC>(H, mask, addend, out, B, N, cfg, st);
 }
 
 template <typename T>
@@ -148,14 +139,9 @@ static int agg_mask_dispatch(const T* H, const uint32_t* mask, const T* addend, 
   if (F == 16 && N <= 20 && aligned && B > 0) {
     // small graphs: dense predicated gather-reduce (profiles/agg_variants_r01.txt)
     if (N <= 8 && agg_fast_fits<T>(N, 8, add, kAggWarps, 1)) return launch_fast<T, 8, 1>(H, mask, addend, out, B, N, independent, st);
-    // 8 < N <= 20: set-bit / clear-bit walk against the graph's column total (see agg_kernels.cuh)
-    const bool walk = agg_walk_mode() != 0;
     if (N == 20 && agg_fast_fits<T>(N, 2, add, kAggWarps, 1))       // the north-star shape: compile-time N
-      return walk ? launch_fast<T, 5, 4, 20, true>(H, mask, addend, out, B, N, independent, st)
-                  : launch_fast<T, 5, 4, 20>(H, mask, addend, out, B, N, independent, st);
-    if (agg_fast_fits<T>(N, 2, add, kAggWarps, 1))
-      return walk ? launch_fast<T, 5, 4, 0, true>(H, mask, addend, out, B, N, independent, st)
-                  : launch_fast<T, 5, 4>(H, mask, addend, out, B, N, independent, st);
+      return launch_fast<T, 5, 4, 20>(H, mask, addend, out, B, N, independent, st);
+    if (agg_fast_fits<T>(N, 2, add, kAggWarps, 1)) return launch_fast<T, 5, 4>(H, mask, addend, out, B, N, independent, st);
   }
   if (F == 16 && N <= 256 && aligned && B > 0) {
     // larger graphs: set-bit / clear-bit walk (work ~ N * min(deg, N - deg)); one warp per graph tile up to

@@ -113,7 +113,7 @@ struct v2v_brain {
 
 static FusedShape fused_shape(const v2v_brain* b) {
   FusedShape s;
-  s.N = b->N; s.Dn = b->Dn; s.De = b->De; s.F = b->F; s.CH = b->CH; s.S = b->S;
+  s.N = b->N; s.Dn = b->Dn; s.De = b->De; s.F = b->F; s.CH = b->CH; s.S = b->S; s.G = b->G;
   s.H1 = b->cfg.hidden[0]; s.H2 = b->cfg.hidden[1]; s.H3 = b->cfg.hidden[2];
   s.layer_K = b->lK.data(); s.layer_O = b->lO.data(); s.w_off = b->lw.data(); s.b_off = b->lb.data();
   s.n_layers = b->n_layers; s.n_params = b->n_params;
@@ -249,7 +249,8 @@ extern "C" int v2v_brain_create(const v2v_brain_config* cfg, v2v_brain** out) {
   }
   for (auto& p : b->params) cudaMemset(p, 0, b->n_params * sizeof(float));
   for (auto& L : b->layers) { b->lK.push_back(L.K); b->lO.push_back(L.n_out); b->lw.push_back(L.w_off); b->lb.push_back(L.b_off); }
-  if (b->G == 1 && b->N <= 32) {
+  // fused whole-network kernel: shared weights up to N = 32, per-slot weights (the reference's model) up to N = 8
+  if ((b->G == 1 && b->N <= 32) || (b->G == b->N && b->N <= 8)) {
     FusedProgram* probe = new FusedProgram();
     if (fused_build_program(fused_shape(b), 1, 1, probe) == 0 && fused_smem_bytes(*probe) <= 226 * 1024) {
       b->partial_ctas = sm_count();
@@ -261,6 +262,8 @@ extern "C" int v2v_brain_create(const v2v_brain_config* cfg, v2v_brain** out) {
     }
     delete probe;
     last_error().clear();
+  }
+  if (b->G == 1 && b->N <= 32) {
     // tensor-core forward plan (predict at large batch)
     TcShape ts;
     ts.N = b->N; ts.Dn = b->Dn; ts.De = b->De; ts.F = b->F; ts.CH = b->CH; ts.S = b->S;
@@ -422,17 +425,18 @@ extern "C" int v2v_tt_plan(const v2v_brain_config* cfg, int* info8) {
 extern "C" int v2v_fused_plan(const v2v_brain_config* cfg, int B, int train, int* info8) {
   V2V_REQUIRE(cfg && info8 && B > 0, "v2v_fused_plan: bad argument");
   for (int i = 0; i < 8; ++i) info8[i] = 0;
-  if (cfg->per_slot || cfg->num_d2d > 32) return 0;
+  if (cfg->num_d2d > 32 || (cfg->per_slot && cfg->num_d2d > 8)) return 0;
+  const int G = cfg->per_slot ? cfg->num_d2d : 1;
   std::vector<int> lK, lO;
   std::vector<size_t> lw, lb;
   size_t off = 0;
-  auto add_layer = [&](int K, int O) { lK.push_back(K); lO.push_back(O); lw.push_back(off); off += (size_t)K * O; lb.push_back(off); off += O; };
+  auto add_layer = [&](int K, int O) { lK.push_back(K); lO.push_back(O); lw.push_back(off); off += (size_t)G * K * O; lb.push_back(off); off += (size_t)G * O; };
   for (int s = 0; s < cfg->stages; ++s) add_layer((s == 0 ? cfg->node_dim : cfg->feedback + cfg->node_dim) + cfg->edge_dim + cfg->feedback, cfg->feedback);
   int k = cfg->node_dim + 2 * cfg->feedback;
   for (int i = 0; i < 3; ++i) { add_layer(k, cfg->hidden[i]); k = cfg->hidden[i]; }
   add_layer(k, cfg->num_ch);
   FusedShape s;
-  s.N = cfg->num_d2d; s.Dn = cfg->node_dim; s.De = cfg->edge_dim; s.F = cfg->feedback; s.CH = cfg->num_ch; s.S = cfg->stages;
+  s.N = cfg->num_d2d; s.Dn = cfg->node_dim; s.De = cfg->edge_dim; s.F = cfg->feedback; s.CH = cfg->num_ch; s.S = cfg->stages; s.G = G;
   s.H1 = cfg->hidden[0]; s.H2 = cfg->hidden[1]; s.H3 = cfg->hidden[2];
   s.layer_K = lK.data(); s.layer_O = lO.data(); s.w_off = lw.data(); s.b_off = lb.data();
   s.n_layers = (int)lK.size(); s.n_params = off;

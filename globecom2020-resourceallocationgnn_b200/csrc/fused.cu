@@ -45,9 +45,9 @@ struct RowVec<2> {
   __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
 };
 
-template <int TR, int TC>
+template <int TR, int TC, bool SLOT>
 __device__ __forceinline__ void gemm_phase(const FusedOp& op, float* arena, const float* Ws, const int* tab, int RP,
-                                           int tid) {
+                                           int TGp, int tid) {
   const int row_groups = RP / TR;
   const int items = row_groups * (op.O / TC);
   const int4* in_rows4 = reinterpret_cast<const int4*>(tab + op.in_tab);     // padded to a multiple of 4 with zero_row
@@ -57,14 +57,15 @@ __device__ __forceinline__ void gemm_phase(const FusedOp& op, float* arena, cons
   for (int item = tid; item < items; item += kFusedThreads) {
     const int cg = item / row_groups, rg = item - cg * row_groups;
     const int r0 = rg * TR, o0 = cg * TC;
+    const int slot = SLOT ? r0 / TGp : 0;                    // slot-major rows: the TR rows of a tile share a weight set
     float acc[TC][TR];
 #pragma unroll
     for (int j = 0; j < TC; ++j) {
-      const float b = Ws[op.b_off + o0 + j];
+      const float b = Ws[op.b_off + slot * op.slot_b + o0 + j];
 #pragma unroll
       for (int i = 0; i < TR; ++i) acc[j][i] = b;
     }
-    const float* wp = Ws + op.w_off + o0;
+    const float* wp = Ws + op.w_off + slot * op.slot_w + o0;
     const float* xb = arena + r0;
 #pragma unroll 2
     for (int k4 = 0; k4 < K4; ++k4) {
@@ -98,9 +99,10 @@ __device__ __forceinline__ void gemm_phase(const FusedOp& op, float* arena, cons
 }
 
 // Neighbour aggregation inside the arena.  item = (feature f, graph g, target split ms).
-template <int NMAX>
+template <int NMAX, bool SLOT>
 __device__ __forceinline__ void agg_phase(const FusedOp& op, float* arena, const int* tab, const uint32_t* mask_s, int RP,
-                                          int N, int TG, int tid) {
+                                          int N, int TG, int TGp, int tid) {
+  const int row_g = SLOT ? 1 : N, row_n = SLOT ? TGp : 1;      // node (g, n) is arena row g * row_g + n * row_n
   constexpr int MS = 3;
   constexpr int MT = (NMAX + MS - 1) / MS;
   const int F = op.K;
@@ -109,10 +111,10 @@ __device__ __forceinline__ void agg_phase(const FusedOp& op, float* arena, const
     const int f = item % F;
     const int rest = item / F;
     const int g = rest % TG, ms = rest / TG;
-    const float* src = arena + tab[op.in_tab + f] * RP + g * N;
+    const float* src = arena + tab[op.in_tab + f] * RP + g * row_g;
     float v[NMAX];
 #pragma unroll
-    for (int n = 0; n < NMAX; ++n) v[n] = (n < N) ? src[n] : 0.f;
+    for (int n = 0; n < NMAX; ++n) v[n] = (n < N) ? src[n * row_n] : 0.f;
     float acc[MT];
 #pragma unroll
     for (int j = 0; j < MT; ++j) acc[j] = 0.f;
@@ -126,34 +128,44 @@ __device__ __forceinline__ void agg_phase(const FusedOp& op, float* arena, const
       for (int n = 0; n < NMAX; ++n)
         if (msk & (1u << n)) acc[j] += v[n];
     }
-    if (g == 0 && ms == 0)                                  // rows past the tile's last node: exact zeros
-      for (int r = TG * N; r < RP; ++r) arena[tab[op.out_tab + f] * RP + r] = 0.f;
-    float* dst = arena + tab[op.out_tab + f] * RP + g * N;
-    const float* add = op.add_tab >= 0 ? arena + tab[op.add_tab + f] * RP + g * N : nullptr;
-    const float* gate = op.gate_tab >= 0 ? arena + tab[op.gate_tab + f] * RP + g * N : nullptr;
+    if (g == 0 && ms == 0) {                                // padding rows of the tile: exact zeros
+      if (SLOT) {
+        for (int n = 0; n < N; ++n)
+          for (int gp = TG; gp < TGp; ++gp) arena[tab[op.out_tab + f] * RP + n * TGp + gp] = 0.f;
+      } else {
+        for (int r = TG * N; r < RP; ++r) arena[tab[op.out_tab + f] * RP + r] = 0.f;
+      }
+    }
+    float* dst = arena + tab[op.out_tab + f] * RP + g * row_g;
+    const float* add = op.add_tab >= 0 ? arena + tab[op.add_tab + f] * RP + g * row_g : nullptr;
+    const float* gate = op.gate_tab >= 0 ? arena + tab[op.gate_tab + f] * RP + g * row_g : nullptr;
 #pragma unroll
     for (int j = 0; j < MT; ++j) {
       const int m = ms + j * MS;
       if (m < N) {
         float r = acc[j];
-        if (add) r += add[m];
-        if (gate) r = gate[m] > 0.f ? r : 0.f;
-        dst[m] = r;
+        if (add) r += add[m * row_n];
+        if (gate) r = gate[m * row_n] > 0.f ? r : 0.f;
+        dst[m * row_n] = r;
       }
     }
   }
 }
 
 
+template <bool SLOT>
 __device__ __forceinline__ void loss_phase(const FusedProgram* P, float* arena, const int* tab, float* hl_s, int RP,
-                                           int valid_rows, float inv_cnt, int tid) {
+                                           int ng, float inv_cnt, int tid) {
+  const int N = P->N, TGp = P->TGp;
+  const int valid_rows = ng * N;
   const int items = P->CH * RP;
   for (int item = tid; item < items; item += kFusedThreads) {
     const int c = item / RP, r = item - c * RP;
     float* q = arena + tab[P->q_tab + c] * RP + r;
     float* yp = arena + tab[P->y_tab + c] * RP + r;
     float dq = 0.f, hub = 0.f;
-    if (r < valid_rows) {
+    const bool valid = SLOT ? (r % TGp) < ng : r < valid_rows;
+    if (valid) {
       const float e = *q - *yp;
       const float ae = fabsf(e);
       const float quad = fminf(ae, 1.f);
@@ -165,11 +177,12 @@ __device__ __forceinline__ void loss_phase(const FusedProgram* P, float* arena, 
   }
   __syncthreads();
   // per-head sums in a fixed order (one thread per head, graphs then channels): bit-stable loss, no float atomics
-  const int N = P->N;
   if (tid < N) {
     float s = 0.f;
-    for (int r = tid; r < valid_rows; r += N)
+    for (int g = 0; g < ng; ++g) {
+      const int r = SLOT ? tid * TGp + g : g * N + tid;
       for (int c = 0; c < P->CH; ++c) s += arena[tab[P->y_tab + c] * RP + r];
+    }
     hl_s[tid] += s;
   }
 }
@@ -189,7 +202,7 @@ __device__ __forceinline__ void bias_grad(const FusedOp& op, int op_idx, const f
 
 // 4x4 weight-gradient block: a[i*4+j] += sum over rows r = r_begin, r_begin + r_step, ... (4 rows each)
 __device__ __forceinline__ void wgrad_block(const FusedOp& op, const float* arena, const int* tab, int RP, int zero_row,
-                                            int kb, int ob, int r_begin, int r_step, float (&a)[16]) {
+                                            int kb, int ob, int r_begin, int r_step, int r_end, float (&a)[16]) {
   const int OB = op.O >> 2;
   const float* xr[4];
   const float* dr[4];
@@ -200,7 +213,7 @@ __device__ __forceinline__ void wgrad_block(const FusedOp& op, const float* aren
     dr[i] = arena + tab[op.dz_tab + ob + i * OB] * RP;      // strided columns: the lanes of a warp hit consecutive rows
   }
 #pragma unroll 2
-  for (int r = r_begin; r < RP; r += r_step) {
+  for (int r = r_begin; r < r_end; r += r_step) {
     float4 xv[4], dv[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -227,16 +240,49 @@ __device__ __forceinline__ void wgrad_block(const FusedOp& op, const float* aren
   }
 }
 
+template <bool SLOT>
 __device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* arena, const float* Ws, const int* tab, int RP,
                                           int zero_row, int tid, const int (&my_blk)[kFusedBlkPerThread],
                                           float (&wacc)[kFusedBlkPerThread][16], int my_bias, float& bacc, float* dWs,
-                                          int* dx_ctr) {
+                                          int* dx_ctr, int G, int TGp, float* part) {
   // ---- weight gradient.  Large layers: 4x4 blocks owned by fixed threads, accumulated in registers across
   // tiles.  Small layers (op.nwt = RS > 0): every block is split over RS adjacent lanes by row groups, reduced
   // with shuffles, and the first lane adds the block into the CTA's shared accumulator (one owner per
   // address: deterministic) -- otherwise a 5..48-block layer would leave most of the CTA idle.
-  int owners_begin, owners_n;
-  if (op.nwt > 0) {
+  int owners_begin = 0, owners_n = 0;
+  if (SLOT) {
+    // per-slot weights: block (slot, kb, ob) sums over the TGp rows of its slot and is added straight into this CTA's
+    // partial row in global memory (one owner per address and tile: deterministic; the row was zeroed in the prologue)
+    const int OB = op.O >> 2, KB = (op.K + 3) >> 2;
+    const int per_slot = KB * OB;
+    for (int blk = tid; blk < G * per_slot; blk += kFusedThreads) {
+      const int slot = blk / per_slot, rem = blk - slot * per_slot;
+      const int kb = rem / OB, ob = rem - kb * OB;
+      float a[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] = 0.f;
+      wgrad_block(op, arena, tab, RP, zero_row, kb, ob, slot * TGp, 4, (slot + 1) * TGp, a);
+      float* dst = part + op.w_off + slot * op.slot_w;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = kb * 4 + i;
+        if (k < op.K) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[k * op.O + ob + j * OB] += a[i * 4 + j];
+        }
+      }
+    }
+    for (int idx = tid; idx < G * op.O; idx += kFusedThreads) {
+      const int slot = idx / op.O, o = idx - slot * op.O;
+      const float* dz = arena + tab[op.dz_tab + o] * RP + slot * TGp;
+      float sb = 0.f;
+      for (int r = 0; r < TGp; r += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(dz + r);
+        sb += (t.x + t.y) + (t.z + t.w);
+      }
+      part[op.b_off + slot * op.slot_b + o] += sb;
+    }
+  } else if (op.nwt > 0) {
     const int RS = op.nwt, OB = op.O >> 2;
     const int tasks = op.nblk * RS;
     const int blk = tid / RS, split = tid - blk * RS;
@@ -244,7 +290,7 @@ __device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* 
 #pragma unroll
     for (int i = 0; i < 16; ++i) a[i] = 0.f;
     const int kb = blk / OB, ob = blk - kb * OB;
-    if (tid < tasks) wgrad_block(op, arena, tab, RP, zero_row, kb, ob, split * 4, RS * 4, a);
+    if (tid < tasks) wgrad_block(op, arena, tab, RP, zero_row, kb, ob, split * 4, RS * 4, RP, a);
     for (int off = RS >> 1; off > 0; off >>= 1) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], off);
@@ -269,7 +315,7 @@ __device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* 
         float a[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) a[i] = 0.f;
-        wgrad_block(op, arena, tab, RP, zero_row, (my_blk[s] >> 8) & 0xff, my_blk[s] & 0xff, 0, 4, a);
+        wgrad_block(op, arena, tab, RP, zero_row, (my_blk[s] >> 8) & 0xff, my_blk[s] & 0xff, 0, 4, RP, a);
 #pragma unroll
         for (int i = 0; i < 16; ++i) wacc[s][i] += a[i];
       }
@@ -277,7 +323,7 @@ __device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* 
     owners_begin = op.blk0 % kFusedThreads;
     owners_n = min(op.nblk, kFusedThreads);
   }
-  bias_grad(op, op_idx, arena, tab, RP, my_bias, bacc);
+  if (!SLOT) bias_grad(op, op_idx, arena, tab, RP, my_bias, bacc);
   // ---- data gradient of the requested input columns (4 rows x 4 columns per item)
   if (op.n_dx > 0) {
     const int row_groups = RP / 4;
@@ -292,8 +338,9 @@ __device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* 
       const int kg = item / row_groups, rg = item - kg * row_groups;
       const int r0 = rg * 4;
       const float* wr[4];
+      const int wslot = SLOT ? (r0 / TGp) * op.slot_w : 0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) wr[i] = Ws + op.w_off + tab[op.dxk_tab + kg * 4 + i] * op.O;
+      for (int i = 0; i < 4; ++i) wr[i] = Ws + op.w_off + wslot + tab[op.dxk_tab + kg * 4 + i] * op.O;
       float4 acc[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -345,7 +392,7 @@ __device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* 
 
 __device__ long long* g_fused_trace = nullptr;       // optional per-phase clock trace of CTA 0 (profiling aid)
 
-template <int NMAX>
+template <int NMAX, bool SLOT>
 __global__ void __launch_bounds__(kFusedThreads, 1)
 fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__ params, const float* __restrict__ node,
                    const float* __restrict__ edge, const uint32_t* __restrict__ in_mask,
@@ -356,15 +403,20 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
   const int tid = threadIdx.x;
   if (tid < 2) dx_ctr[tid] = 0;
   const int N = P->N, TG = P->TG, RP = P->RP, CH = P->CH, Dn = P->Dn, De = P->De;
+  const int G = P->G, TGp = P->TGp, row_g = P->row_g, row_n = P->row_n;
   const int n_params = P->n_params, n_ops = P->n_ops, n_tab = P->n_tab, train = P->train;
-  const int np_pad = (n_params + 3) & ~3;
-  float* Ws = smem;
-  int* tab = reinterpret_cast<int*>(Ws + np_pad);
+  // shared weights live in shared memory; per-slot weights (G x as many: 151 KB at the reference's N = 4) stay in global
+  // memory / L2 and are read through the read-only path (a warp reads one broadcast vector per k)
+  const int np_pad = SLOT ? 0 : ((n_params + 3) & ~3);
+  float* Ws_s = smem;
+  const float* Ws = SLOT ? params : Ws_s;
+  int* tab = reinterpret_cast<int*>(Ws_s + np_pad);
   FusedOp* ops = reinterpret_cast<FusedOp*>(tab + ((n_tab + 3) & ~3));
   uint32_t* mask_s = reinterpret_cast<uint32_t*>(ops + n_ops);
   float* hl_s = reinterpret_cast<float*>(mask_s + ((2 * TG * N + 3) & ~3));
   float* dWs = hl_s + 32;                                   // shared weight-gradient accumulator of the small layers
   float* arena = dWs + P->n_small;
+  float* part = (train && partial) ? partial + (size_t)blockIdx.x * (n_params + kFusedPartialTail) : nullptr;
 
   // programmatic dependent launch: everything up to griddepcontrol.wait overlaps the tail of the preceding kernel
   // (normally the previous step's reduce/Adam); it only reads the immutable program and writes shared memory
@@ -380,9 +432,13 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
   for (int i = tid; i < P->n_rows * RP / 4; i += kFusedThreads)      // whole arena: finite everywhere, zero row included
     reinterpret_cast<float4*>(arena)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  for (int i = tid; i < n_params / 4; i += kFusedThreads)
-    reinterpret_cast<float4*>(Ws)[i] = reinterpret_cast<const float4*>(params)[i];
-  for (int i = (n_params & ~3) + tid; i < n_params; i += kFusedThreads) Ws[i] = params[i];
+  if (!SLOT) {
+    for (int i = tid; i < n_params / 4; i += kFusedThreads)
+      reinterpret_cast<float4*>(Ws_s)[i] = reinterpret_cast<const float4*>(params)[i];
+    for (int i = (n_params & ~3) + tid; i < n_params; i += kFusedThreads) Ws_s[i] = params[i];
+  } else if (train) {
+    for (int i = tid; i < n_params; i += kFusedThreads) part[i] = 0.f;   // weight-gradient blocks are added tile by tile
+  }
 
   // the whole grid is resident (one CTA per SM): let the dependent reduce/Adam kernel be scheduled now, its CTAs
   // park in griddepcontrol.wait until this grid has completed and flushed
@@ -393,12 +449,12 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
 #pragma unroll
   for (int s = 0; s < kFusedBlkPerThread; ++s) {
     const int b = tid + s * kFusedThreads;
-    my_blk[s] = (train && b < P->n_blocks) ? P->blk_info[b] : 0;
+    my_blk[s] = (!SLOT && train && b < P->n_blocks) ? P->blk_info[b] : 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) wacc[s][i] = 0.f;
   }
   const int bias_slot = kFusedThreads - 1 - tid;
-  const int my_bias = (train && bias_slot < P->n_bias) ? P->bias_info[bias_slot] : -1;
+  const int my_bias = (!SLOT && train && bias_slot < P->n_bias) ? P->bias_info[bias_slot] : -1;
   float bacc = 0.f;
 
   const int n_tiles = (B + TG - 1) / TG;
@@ -407,7 +463,7 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
     const int ng = min(TG, B - g0);
     const int valid_rows = ng * N;
     __syncthreads();                         // previous tile fully consumed (and the prologue stores)
-    {
+    if (!SLOT) {
       const float* nsrc = node + (size_t)g0 * N * Dn;
       for (int idx = tid; idx < RP * Dn; idx += kFusedThreads) {
         const int r = idx / Dn, f = idx - r * Dn;
@@ -418,10 +474,6 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
         const int r = idx / De, f = idx - r * De;
         arena[(P->x0_row0 + Dn + f) * RP + r] = (r < valid_rows) ? esrc[idx] : 0.f;
       }
-      for (int idx = tid; idx < TG * N; idx += kFusedThreads) {
-        mask_s[idx] = (idx < valid_rows) ? in_mask[(size_t)g0 * N + idx] : 0u;
-        if (train) mask_s[TG * N + idx] = (idx < valid_rows) ? out_mask[(size_t)g0 * N + idx] : 0u;
-      }
       if (train) {
         const float* ysrc = y + (size_t)g0 * N * CH;
         for (int idx = tid; idx < RP * CH; idx += kFusedThreads) {
@@ -429,6 +481,31 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
           arena[tab[P->y_tab + c] * RP + r] = (r < valid_rows) ? ysrc[idx] : 0.f;
         }
       }
+    } else {                                 // slot-major rows: node (g, n) -> row n * TGp + g
+      const float* nsrc = node + (size_t)g0 * N * Dn;
+      for (int idx = tid; idx < TG * N * Dn; idx += kFusedThreads) {
+        const int gn = idx / Dn, f = idx - gn * Dn;
+        const int g = gn / N, n = gn - g * N;
+        arena[(P->x0_row0 + f) * RP + g * row_g + n * row_n] = (g < ng) ? nsrc[idx] : 0.f;
+      }
+      const float* esrc = edge + (size_t)g0 * N * De;
+      for (int idx = tid; idx < TG * N * De; idx += kFusedThreads) {
+        const int gn = idx / De, f = idx - gn * De;
+        const int g = gn / N, n = gn - g * N;
+        arena[(P->x0_row0 + Dn + f) * RP + g * row_g + n * row_n] = (g < ng) ? esrc[idx] : 0.f;
+      }
+      if (train) {
+        const float* ysrc = y + (size_t)g0 * N * CH;
+        for (int idx = tid; idx < TG * N * CH; idx += kFusedThreads) {
+          const int gn = idx / CH, c = idx - gn * CH;
+          const int g = gn / N, n = gn - g * N;
+          arena[tab[P->y_tab + c] * RP + g * row_g + n * row_n] = (g < ng) ? ysrc[idx] : 0.f;
+        }
+      }
+    }
+    for (int idx = tid; idx < TG * N; idx += kFusedThreads) {
+      mask_s[idx] = (idx < valid_rows) ? in_mask[(size_t)g0 * N + idx] : 0u;
+      if (train) mask_s[TG * N + idx] = (idx < valid_rows) ? out_mask[(size_t)g0 * N + idx] : 0u;
     }
     __syncthreads();
     // profiling aid: lane 0 of every warp of CTA 0 records [phase][warp] = {work done, barrier released}
@@ -440,14 +517,14 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
       switch (op.type) {
         case FOP_GEMM: {
           const int rg4 = RP / 4;
-          if (op.O % 8 == 0 && rg4 * (op.O / 8) >= (kFusedThreads * 3) / 4) gemm_phase<4, 8>(op, arena, Ws, tab, RP, tid);
-          else if (rg4 * (op.O / 4) >= kFusedThreads / 2) gemm_phase<4, 4>(op, arena, Ws, tab, RP, tid);
-          else gemm_phase<2, 4>(op, arena, Ws, tab, RP, tid);
+          if (op.O % 8 == 0 && rg4 * (op.O / 8) >= (kFusedThreads * 3) / 4) gemm_phase<4, 8, SLOT>(op, arena, Ws, tab, RP, TGp, tid);
+          else if (SLOT || rg4 * (op.O / 4) >= kFusedThreads / 2) gemm_phase<4, 4, SLOT>(op, arena, Ws, tab, RP, TGp, tid);
+          else gemm_phase<2, 4, SLOT>(op, arena, Ws, tab, RP, TGp, tid);
           break;
         }
-        case FOP_AGG: agg_phase<NMAX>(op, arena, tab, mask_s, RP, N, TG, tid); break;
-        case FOP_LOSS: loss_phase(P, arena, tab, hl_s, RP, valid_rows, inv_cnt, tid); break;
-        case FOP_BWD: bwd_phase(op, oi, arena, Ws, tab, RP, P->zero_row, tid, my_blk, wacc, my_bias, bacc, dWs, &dx_ctr[oi & 1]); break;
+        case FOP_AGG: agg_phase<NMAX, SLOT>(op, arena, tab, mask_s, RP, N, TG, TGp, tid); break;
+        case FOP_LOSS: loss_phase<SLOT>(P, arena, tab, hl_s, RP, ng, inv_cnt, tid); break;
+        case FOP_BWD: bwd_phase<SLOT>(op, oi, arena, Ws, tab, RP, P->zero_row, tid, my_blk, wacc, my_bias, bacc, dWs, &dx_ctr[oi & 1], G, TGp, part); break;
         default: break;
       }
       if (trace) trace[((oi + 1) * kFusedWarps + warp) * 2] = clock64();
@@ -457,37 +534,39 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
     if (!train) {
       float* qdst = q_out + (size_t)g0 * N * CH;
       for (int idx = tid; idx < valid_rows * CH; idx += kFusedThreads) {
-        const int r = idx / CH, c = idx - r * CH;
-        qdst[idx] = arena[tab[P->q_tab + c] * RP + r];
+        const int gn = idx / CH, c = idx - gn * CH;
+        const int g = gn / N, n = gn - g * N;
+        qdst[idx] = arena[tab[P->q_tab + c] * RP + g * row_g + n * row_n];
       }
     }
   }
 
   if (train) {
     float* dst = partial + (size_t)blockIdx.x * (n_params + kFusedPartialTail);
+    if (!SLOT) {
 #pragma unroll
-    for (int s = 0; s < kFusedBlkPerThread; ++s) {
-      const int b = tid + s * kFusedThreads;
-      if (b < P->n_blocks) {
-        const FusedOp& op = ops[my_blk[s] >> 16];
-        const int kb = (my_blk[s] >> 8) & 0xff, ob = my_blk[s] & 0xff;
+      for (int s = 0; s < kFusedBlkPerThread; ++s) {
+        const int b = tid + s * kFusedThreads;
+        if (b < P->n_blocks) {
+          const FusedOp& op = ops[my_blk[s] >> 16];
+          const int kb = (my_blk[s] >> 8) & 0xff, ob = my_blk[s] & 0xff;
+          const int OB = op.O >> 2;
+          for (int i = 0; i < 4; ++i) {
+            const int k = kb * 4 + i;
+            if (k < op.K) {
 #pragma unroll
-        const int OB = op.O >> 2;
-        for (int i = 0; i < 4; ++i) {
-          const int k = kb * 4 + i;
-          if (k < op.K) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[op.w_off + k * op.O + ob + j * OB] = wacc[s][i * 4 + j];
+              for (int j = 0; j < 4; ++j) dst[op.w_off + k * op.O + ob + j * OB] = wacc[s][i * 4 + j];
+            }
           }
         }
       }
-    }
-    if (my_bias >= 0) dst[ops[my_bias >> 16].b_off + (my_bias & 0xffff)] = bacc;
-    __syncthreads();
-    for (int oi = 0; oi < n_ops; ++oi) {
-      const FusedOp& op = ops[oi];
-      if (op.type == FOP_BWD && op.nwt > 0)
-        for (int i = tid; i < op.K * op.O; i += kFusedThreads) dst[op.w_off + i] = dWs[op.wt0 + i];
+      if (my_bias >= 0) dst[ops[my_bias >> 16].b_off + (my_bias & 0xffff)] = bacc;
+      __syncthreads();
+      for (int oi = 0; oi < n_ops; ++oi) {
+        const FusedOp& op = ops[oi];
+        if (op.type == FOP_BWD && op.nwt > 0)
+          for (int i = tid; i < op.K * op.O; i += kFusedThreads) dst[op.w_off + i] = dWs[op.wt0 + i];
+      }
     }
     __syncthreads();
     if (tid < kFusedPartialTail) dst[n_params + tid] = (tid < N) ? hl_s[tid] * inv_cnt : 0.f;   // per-head Huber sums
@@ -597,13 +676,20 @@ std::vector<int> iota(int first, int n) {
 int fused_build_program(const FusedShape& s, int TG, int train, FusedProgram* out) {
   V2V_REQUIRE(s.N <= 32 && s.F % 4 == 0 && s.CH % 4 == 0 && s.H1 % 4 == 0 && s.H2 % 4 == 0 && s.H3 % 4 == 0,
               "fused path: unsupported dimensions");
+  V2V_REQUIRE(s.G == 1 || s.G == s.N, "fused path: weight groups must be 1 (shared) or N (per slot)");
+  const bool slot = s.G > 1;
   V2V_REQUIRE(s.n_layers == s.S + 4 && s.S >= 1, "fused path: unexpected layer count");
   for (int l = 0; l < s.n_layers; ++l)
     V2V_REQUIRE(s.w_off[l] % 4 == 0 && s.b_off[l] % 4 == 0 && s.layer_K[l] <= 255 && s.layer_O[l] <= 1020,
                 "fused path: unaligned parameter layout");
   FusedProgram* P = out;
   *P = FusedProgram{};
-  P->N = s.N; P->TG = TG; P->R = TG * s.N; P->RP = (P->R + 3) & ~3; P->CH = s.CH; P->F = s.F;
+  P->N = s.N; P->TG = TG; P->R = TG * s.N; P->CH = s.CH; P->F = s.F;
+  P->G = s.G;
+  P->TGp = slot ? ((TG + 3) & ~3) : 0;
+  P->RP = slot ? s.N * P->TGp : ((P->R + 3) & ~3);
+  P->row_g = slot ? 1 : s.N;
+  P->row_n = slot ? P->TGp : 1;
   P->Dn = s.Dn; P->De = s.De; P->n_params = (int)s.n_params; P->train = train;
   Builder b; b.P = P;
   const int F = s.F, Dn = s.Dn, De = s.De, S = s.S;
@@ -622,6 +708,7 @@ int fused_build_program(const FusedShape& s, int TG, int train, FusedProgram* ou
     FusedOp* g = b.add_op();
     g->type = FOP_GEMM; g->in_tab = b.tab_put(gemm_in[st]); g->K = (int)gemm_in[st].size();
     g->out_tab = b.tab_put(h[st]); g->O = F; g->w_off = (int)s.w_off[st]; g->b_off = (int)s.b_off[st];
+    g->slot_w = s.layer_K[st] * s.layer_O[st]; g->slot_b = s.layer_O[st];
     g->relu = st < S - 1;
     FusedOp* ag = b.add_op();
     ag->type = FOP_AGG; ag->in_tab = b.tab_put(h[st]); ag->K = F; ag->out_tab = b.tab_put(a[st]); ag->O = F;
@@ -636,6 +723,7 @@ int fused_build_program(const FusedShape& s, int TG, int train, FusedProgram* ou
     FusedOp* g = b.add_op();
     g->type = FOP_GEMM; g->in_tab = b.tab_put(gemm_in[l]); g->K = (int)gemm_in[l].size();
     g->out_tab = b.tab_put(mrows[j]); g->O = widths[j]; g->w_off = (int)s.w_off[l]; g->b_off = (int)s.b_off[l];
+    g->slot_w = s.layer_K[l] * s.layer_O[l]; g->slot_b = s.layer_O[l];
     g->relu = j < 3;
   }
   P->q_tab = b.tab_put(mrows[3]);
@@ -661,6 +749,7 @@ int fused_build_program(const FusedShape& s, int TG, int train, FusedProgram* ou
       o->type = FOP_BWD;
       o->in_tab = b.tab_put(gemm_in[l]); o->K = (int)gemm_in[l].size();
       o->O = s.layer_O[l]; o->w_off = (int)s.w_off[l]; o->b_off = (int)s.b_off[l];
+      o->slot_w = s.layer_K[l] * s.layer_O[l]; o->slot_b = s.layer_O[l];
       o->dz_tab = b.tab_put(dz);
       o->n_dx = (int)dxk.size();
       if (o->n_dx) { o->dxk_tab = b.tab_put(dxk); o->dx_tab = b.tab_put(dx); }
@@ -668,6 +757,10 @@ int fused_build_program(const FusedShape& s, int TG, int train, FusedProgram* ou
       o->blk0 = blk;
       const int kb_n = (o->K + 3) / 4, ob_n = o->O / 4;
       o->nblk = kb_n * ob_n;
+      if (slot) {                  // per-slot weights: blocks go straight to the CTA's partial row (bwd_phase<SLOT>)
+        o->blk0 = -1; o->nblk = 0; o->wt0 = 0; o->nwt = 0; o->bias0 = 0;
+        return op_idx;
+      }
       const bool small = (l != reg_layer);
       if (small) {                 // row-split weight gradient into the shared accumulator (wt0 = offset, nwt = RS)
         int rs = 1;
@@ -735,7 +828,7 @@ int fused_build_program(const FusedShape& s, int TG, int train, FusedProgram* ou
 
 size_t fused_smem_bytes(const FusedProgram& p) {
   size_t words = 0;
-  words += (p.n_params + 3) & ~3;
+  if (p.G == 1) words += (p.n_params + 3) & ~3;       // per-slot weights stay in global memory
   words += (p.n_tab + 3) & ~3;
   words += (size_t)p.n_ops * (sizeof(FusedOp) / 4);
   words += (2 * p.TG * p.N + 3) & ~3;
@@ -762,7 +855,7 @@ int fused_pick_tg(const FusedShape& s, int B, int train) {
   for (int tg = 1; tg <= fit; ++tg) {
     const int tiles = ceil_div(B, tg);
     const int rounds = ceil_div(tiles, sms);
-    const int rp = (tg * s.N + 3) & ~3;
+    const int rp = s.G > 1 ? s.N * ((tg + 3) & ~3) : ((tg * s.N + 3) & ~3);
     const double cost = rounds * (rp + 24.0);        // rows per tile + fixed per-tile overhead (barriers, loads)
     if (cost < best_cost - 1e-9) { best_cost = cost; best = tg; }
   }
@@ -771,7 +864,7 @@ int fused_pick_tg(const FusedShape& s, int B, int train) {
 
 int fused_grid(const FusedProgram& p, int B) { return std::max(1, std::min(ceil_div(B, p.TG), sm_count())); }
 
-template <int NMAX>
+template <int NMAX, bool SLOT>
 static int fused_launch_t(const FusedProgram& ph, const FusedProgram* prog_dev, const float* params, const float* node,
                           const float* edge, const uint32_t* in_mask, const uint32_t* out_mask, const float* y, float* q_out,
                           float* partial_dev, float* head_loss, int B, int grid, cudaStream_t st) {
@@ -779,7 +872,7 @@ static int fused_launch_t(const FusedProgram& ph, const FusedProgram* prog_dev, 
   const float inv_cnt = 1.f / ((float)B * (float)ph.CH);
   static size_t smem_set = 0;                  // per instantiation (NMAX): every kernel needs its own opt-in
   if (smem > smem_set) {
-    V2V_CHECK_CUDA(cudaFuncSetAttribute(fused_brain_kernel<NMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    V2V_CHECK_CUDA(cudaFuncSetAttribute(fused_brain_kernel<NMAX, SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
   cudaLaunchConfig_t lc{};
@@ -792,7 +885,7 @@ static int fused_launch_t(const FusedProgram& ph, const FusedProgram* prog_dev, 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = attr;
   lc.numAttrs = 1;
-  V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, fused_brain_kernel<NMAX>, prog_dev, params, node, edge, in_mask, out_mask, y, q_out,
+  V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, fused_brain_kernel<NMAX, SLOT>, prog_dev, params, node, edge, in_mask, out_mask, y, q_out,
                                     partial_dev, head_loss, B, inv_cnt));
   return launch_status("fused_brain_kernel");
 }
@@ -801,10 +894,14 @@ int fused_launch(const FusedProgram& ph, const FusedProgram* prog_dev, const flo
                  const float* edge, const uint32_t* in_mask, const uint32_t* out_mask, const float* y, float* q_out,
                  float* partial_dev, float* head_loss, int B, int grid, cudaStream_t st) {
 #define V2V_FUSED_ARGS ph, prog_dev, params, node, edge, in_mask, out_mask, y, q_out, partial_dev, head_loss, B, grid, st
-  if (ph.N <= 4) return fused_launch_t<4>(V2V_FUSED_ARGS);
-  if (ph.N <= 8) return fused_launch_t<8>(V2V_FUSED_ARGS);
-  if (ph.N <= 20) return fused_launch_t<20>(V2V_FUSED_ARGS);
-  return fused_launch_t<32>(V2V_FUSED_ARGS);
+  if (ph.G > 1) {                                        // per-slot weights (the reference's model; N <= 8 here)
+    if (ph.N <= 4) return fused_launch_t<4, true>(V2V_FUSED_ARGS);
+    return fused_launch_t<8, true>(V2V_FUSED_ARGS);
+  }
+  if (ph.N <= 4) return fused_launch_t<4, false>(V2V_FUSED_ARGS);
+  if (ph.N <= 8) return fused_launch_t<8, false>(V2V_FUSED_ARGS);
+  if (ph.N <= 20) return fused_launch_t<20, false>(V2V_FUSED_ARGS);
+  return fused_launch_t<32, false>(V2V_FUSED_ARGS);
 #undef V2V_FUSED_ARGS
 }
 

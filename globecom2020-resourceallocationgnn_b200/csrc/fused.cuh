@@ -28,8 +28,9 @@ struct FusedOp {
   int blk0, nblk;         // BWD: range of global weight-gradient block ids of this layer
   int bias0;              // BWD: first global bias-gradient slot of this layer
   int wt0, nwt;           // BWD: nwt = RS > 0 marks a small layer (blocks split over RS lanes by rows), wt0 = its offset in
-                          // the shared accumulator dWs (sizeof(FusedOp) stays a multiple of 16 bytes)
-                          // (sizeof(FusedOp) stays a multiple of 16 bytes: shared-memory carve-up alignment)
+                          // the shared accumulator dWs
+  int slot_w, slot_b;     // per-slot weights (G == N): floats between the W / bias of consecutive node slots
+  int pad_[2];            // (sizeof(FusedOp) stays a multiple of 16 bytes: shared-memory carve-up alignment)
 };
 static_assert(sizeof(FusedOp) % 16 == 0, "FusedOp must stay 16-byte sized");
 
@@ -52,6 +53,10 @@ struct FusedProgram {
   int n_bias;             // bias-gradient slots over all layers
   int train;              // 1: loss + backward, 0: forward only
   int n_small;            // floats of the shared weight-gradient accumulator (small layers)
+  // Row layout of a tile.  Shared weights (G == 1): graph-major, node (g, n) is arena row g * N + n.  Per-slot weights
+  // (G == N, the reference's model, BS_brain.py:121-200): slot-major, row n * TGp + g with TGp = TG rounded up to 4, so
+  // that the 4 rows of a register tile always share one weight set.
+  int G, TGp, row_g, row_n;
   FusedOp ops[kFusedMaxOps];
   int tab[kFusedMaxTab];
   // block b -> op index, k0, o0 (packed: op<<16 | k0<<8 | o0), bias slot -> op<<16 | o
@@ -63,6 +68,7 @@ struct FusedProgram {
 // the configuration is outside the fused path (then the layered kernels are used).
 struct FusedShape {
   int N, Dn, De, F, CH, S, H1, H2, H3;
+  int G;                   // 1: shared weights, N: one weight set per node slot
   const int* layer_K;      // stacked weight rows per layer
   const int* layer_O;
   const size_t* w_off;

@@ -12,15 +12,15 @@ timeout 300 python bench.py --config c3 --scaling strong --steps 100 --warmup 10
 timeout 300 python bench.py --config c1 > $O/bench_c1_$TAG.json 2> $O/bench_c1_$TAG.err; echo "c1 rc=$?"; tail -2 $O/bench_c1_$TAG.err
 timeout 300 python bench.py --config c4 > $O/bench_c4_$TAG.json 2> $O/bench_c4_$TAG.err; echo "c4 rc=$?"; tail -2 $O/bench_c4_$TAG.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches_$TAG.csv \
-   python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $O/ncu_launches_$TAG.log 2>&1; echo "ncu launches rc=$?"
+   python bench.py --steps 20 --warmup 3 --pool 4 --no-cpu-baseline --no-roofline > $O/ncu_launches_$TAG.log 2>&1; echo "ncu launches rc=$?"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_c3_$TAG.csv \
-   python bench.py --config c3 --steps 20 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_launches_c3_$TAG.log 2>&1; echo "ncu launches c3 rc=$?"
+   python bench.py --config c3 --steps 20 --warmup 3 --pool 4 --no-cpu-baseline --no-roofline --no-e2e > $O/ncu_launches_c3_$TAG.log 2>&1; echo "ncu launches c3 rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:agg_mask -c 2 -o $O/agg_full_$TAG -f \
    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_agg_$TAG.log 2>&1; echo "ncu agg rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:fused_brain -s 200 -c 1 -o $O/fused_full_$TAG -f \
-   python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_fused_$TAG.log 2>&1; echo "ncu fused rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:tt_kernel -s 80 -c 1 -o $O/tt_full_$TAG -f \
-   python bench.py --config c3 --scaling strong --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_tt_$TAG.log 2>&1; echo "ncu tt rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:fused_brain -s 12 -c 1 -o $O/fused_full_$TAG -f \
+   python bench.py --steps 6 --warmup 3 --pool 4 --no-cpu-baseline --no-roofline --no-e2e > $O/ncu_fused_$TAG.log 2>&1; echo "ncu fused rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:tt_kernel -s 12 -c 1 -o $O/tt_full_$TAG -f \
+   python bench.py --config c3 --scaling strong --steps 6 --warmup 3 --pool 4 --no-cpu-baseline --no-roofline --no-e2e > $O/ncu_tt_$TAG.log 2>&1; echo "ncu tt rc=$?"
 python - <<PY
 import json
 for f in ("bench_n1", "bench_ref", "bench_c3_weak_n1", "bench_c3_strong_n1", "bench_c1", "bench_c4"):

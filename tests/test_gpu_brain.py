@@ -141,13 +141,16 @@ def test_forward_backward_vs_live_oracle(v2v, N, S, per_slot, B, kind):
     check_grads(brain.get_flat_params(2), z, q.astype(np.float64))
 
 
-@pytest.mark.parametrize("N,S,B", [(20, 2, 1024), (20, 2, 7), (20, 2, 1), (20, 3, 333), (4, 3, 256), (8, 1, 100), (31, 2, 50),
-                                   (20, 2, 2500)])
-def test_fused_kernel_matches_layered_kernels(v2v, N, S, B):
-    """The one-launch fused network (shared weights) against the layer-by-layer kernels: forward to 1e-5,
-    gradients, one Adam step."""
+@pytest.mark.parametrize("N,S,B,per_slot", [(20, 2, 1024, False), (20, 2, 7, False), (20, 2, 1, False), (20, 3, 333, False),
+                                            (4, 3, 256, False), (8, 1, 100, False), (31, 2, 50, False), (20, 2, 2500, False),
+                                            # the reference's own model: one weight set per node slot (BS_brain.py:121-200)
+                                            (4, 3, 256, True), (4, 3, 1, True), (4, 3, 5, True), (4, 3, 3000, True),
+                                            (7, 2, 333, True), (8, 3, 64, True), (2, 1, 9, True)])
+def test_fused_kernel_matches_layered_kernels(v2v, N, S, B, per_slot):
+    """The one-launch fused network (shared weights, and per-slot weights up to N = 8) against the layer-by-layer
+    kernels: forward to 1e-5, gradients, one Adam step."""
     rng = np.random.default_rng(N * 100 + S * 10 + B)
-    brain = v2v.BS(N, 3, 1, 16, 1, 4, stages=S, per_slot=False, max_batch=B, data_parallel=False, seed=9)
+    brain = v2v.BS(N, 3, 1, 16, 1, 4, stages=S, per_slot=per_slot, max_batch=B, data_parallel=False, seed=9)
     info = brain.fused_info(B)
     assert info["capable"] == 1 and info["smem_bytes"] <= 227 * 1024
     node, edge, adj, _ = O.synth_batch(B, N, rng)
@@ -178,7 +181,7 @@ def test_fused_kernel_matches_layered_kernels(v2v, N, S, B):
         assert np.quantile(np.abs(pf - pl), 0.9) <= 2e-6, mode
     qf = res[1][0]
     # and against the fp64 oracle
-    d = O.BrainDims(N, stages=S, per_slot=False)
+    d = O.BrainDims(N, stages=S, per_slot=per_slot)
     L = O.unflatten_params(d, p0.astype(np.float64))
     qr = O.brain_forward(d, L, node.astype(np.float32).astype(np.float64), edge.astype(np.float32).astype(np.float64), adj)
     assert rel_err(qf, qr) <= RTOL

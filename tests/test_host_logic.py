@@ -93,3 +93,35 @@ def test_tensor_core_plan_host_query(v2v):
     # outside the path: per-slot weights (the reference default), N > 32, layers wider than the tensor-memory regions
     for cfg in (_cfg(v2v, 4, 3, per_slot=1), _cfg(v2v, 40), _cfg(v2v, 20, hidden=(200, 40, 20)), _cfg(v2v, 20, F=12)):
         assert lib.v2v_tc_plan(C.byref(cfg), info) == 0 and info[0] == 0
+
+
+def test_bf16_training_plan_host_query(v2v):
+    """csrc/tc_train.cu's plan is host logic too: steps and MMAs per training tile, shared memory, operand planes."""
+    import ctypes as C
+    lib = v2v.load_library()
+    info = (C.c_int32 * 8)()
+    for N, S in ((20, 3), (20, 2), (4, 3), (32, 1)):
+        assert lib.v2v_tt_plan(C.byref(_cfg(v2v, N, S)), info) == 0
+        capable, tg, steps, mmas, smem, planes, wimg, blocks = list(info)
+        assert capable == 1 and tg == 128 // N
+        assert steps == 2 * S + 8                      # S combine + 4 MLP forward, 3 MLP + S aggregated data gradients, 1 weight gradient
+        # forward k-steps of 16: 1, 3 per later stage, 3, 5, 3, 2; data gradient: 1, 2, 3, 5, 1 per later stage; weight gradient 3 x 8
+        assert mmas == (1 + 3 * (S - 1) + 3 + 5 + 3 + 2) + (1 + 2 + 3 + 5 + (S - 1)) + 24
+        assert smem <= 226 * 1024 and blocks == S + 7
+        assert planes == (2 + 4 * S + 10 + 5 + 3) + (2 * S + 10 + 5 + 3 + 1 + (1 if (2 * S + 19) % 2 else 2))
+        assert wimg == 16 * 16 + (S - 1) * 48 * 16 + 48 * 80 + 80 * 48 + 48 * 32 + 32 * 16
+    for cfg in (_cfg(v2v, 4, 3, per_slot=1), _cfg(v2v, 40), _cfg(v2v, 20, S=4), _cfg(v2v, 20, F=8)):
+        assert lib.v2v_tt_plan(C.byref(cfg), info) == 0 and info[0] == 0
+
+
+def test_fused_plan_per_slot_host_query(v2v):
+    """The fused FP32 kernel's program for the reference's own model (per-slot weights, N = 4, 3 stages): weights stay in
+    global memory, rows are slot-major, so the shared-memory footprint is the arena alone."""
+    import ctypes as C
+    lib = v2v.load_library()
+    info = (C.c_int * 8)()
+    assert lib.v2v_fused_plan(C.byref(_cfg(v2v, 4, 3, per_slot=1)), 256, 1, info) == 0
+    capable, tg, rows, smem, phases, blocks, bias_slots, table = list(info)
+    assert capable == 1 and 1 <= tg <= 64 and smem <= 226 * 1024 and blocks == 0 and bias_slots == 0
+    assert lib.v2v_fused_plan(C.byref(_cfg(v2v, 4, 3, per_slot=0)), 256, 1, info) == 0 and info[5] > 0
+    assert lib.v2v_fused_plan(C.byref(_cfg(v2v, 20, 3, per_slot=1)), 256, 1, info) == 0 and info[0] == 0     # per-slot beyond N = 8: layered
