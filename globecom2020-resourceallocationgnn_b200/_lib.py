@@ -122,6 +122,7 @@ SIGNATURES = {
     "v2v_brain_tensor_core_info": (C.c_int, [c_void_p, c_i32_p]),
     "v2v_tc_plan": (C.c_int, [C.POINTER(BrainConfig), c_i32_p]),
     "v2v_tt_plan": (C.c_int, [C.POINTER(BrainConfig), c_i32_p]),
+    "v2v_tt_set_trace": (C.c_int, [c_void_p]),
     "v2v_brain_tc_debug": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, c_void_p, c_void_p, c_i32_p,
                                      c_void_p]),
     "v2v_host_gather": (C.c_int, [c_view_p, C.c_int, c_void_p, C.c_long, C.c_int, c_i32_p]),

@@ -108,7 +108,6 @@ struct v2v_brain {
   bool bf16 = false;
   TtPlan* tt_plan = nullptr;                    // host copy
   TtPlan* tt_plan_dev = nullptr;
-  void* tt_wimg = nullptr;                      // bf16 weight image + fp32 biases of the last call
 };
 
 static FusedShape fused_shape(const v2v_brain* b) {
@@ -180,7 +179,6 @@ extern "C" void v2v_brain_destroy(v2v_brain* b) {
   cudaFree(b->tc_plan_dev);
   cudaFree(b->tc_wimg);
   cudaFree(b->tt_plan_dev);
-  cudaFree(b->tt_wimg);
   delete b->tt_plan;
   for (auto& kv : b->fused_cache) { cudaFree(kv.second->dev); delete kv.second; }
   delete b;
@@ -285,10 +283,8 @@ extern "C" int v2v_brain_create(const v2v_brain_config* cfg, v2v_brain** out) {
     b->tt_plan = new TtPlan();
     int rc2 = tt_build_plan(ts, b->tt_plan);
     if (rc2 == 0) {
-      const size_t img = (size_t)b->tt_plan->w_elems * 2 + (size_t)b->tt_plan->bias_floats * 4;
       if (cudaMalloc((void**)&b->tt_plan_dev, sizeof(TtPlan)) != cudaSuccess ||
-          cudaMemcpy(b->tt_plan_dev, b->tt_plan, sizeof(TtPlan), cudaMemcpyHostToDevice) != cudaSuccess ||
-          cudaMalloc(&b->tt_wimg, img) != cudaSuccess)
+          cudaMemcpy(b->tt_plan_dev, b->tt_plan, sizeof(TtPlan), cudaMemcpyHostToDevice) != cudaSuccess)
         rc2 = fail("v2v_brain_create: device allocation failed (bf16 plan)");
     }
     if (rc2 == 0 && !b->partial) {
@@ -337,6 +333,7 @@ extern "C" int v2v_brain_set_params(v2v_brain* b, int which, const float* host_i
 }
 
 extern "C" int v2v_fused_set_trace(long long* dev_buf) { return fused_set_trace(dev_buf); }
+extern "C" int v2v_tt_set_trace(long long* dev_buf) { return tt_set_trace(dev_buf); }
 
 extern "C" int v2v_brain_set_fused(v2v_brain* b, int enable) {
   V2V_REQUIRE(b, "v2v_brain_set_fused: null brain");
@@ -516,8 +513,8 @@ extern "C" int v2v_brain_forward(v2v_brain* b, const float* node_dev, const floa
   if (b->bf16) {
     V2V_REQUIRE(in_mask_dev && !neighbor_dev, "v2v_brain_forward: the bf16 brain needs the binary adjacency masks and the "
                 "reference's all-zero neighbour input");
-    return tt_launch(*b->tt_plan, b->tt_plan_dev, b->params[target ? 1 : 0], b->tt_wimg, node_dev, edge_dev, in_mask_dev, nullptr,
-                     nullptr, q_dev, nullptr, B, 0, (cudaStream_t)stream);
+    return tt_launch(*b->tt_plan, b->tt_plan_dev, b->params[target ? 1 : 0], node_dev, edge_dev, in_mask_dev, nullptr, q_dev,
+                     nullptr, B, 0, (cudaStream_t)stream);
   }
   if (b->tc_capable && b->tc_mode > 0 && b->fused_enabled && in_mask_dev && !neighbor_dev &&
       (b->tc_mode >= 2 || ceil_div(B, b->tc_plan.TG) >= 2 * sm_count()))
@@ -554,7 +551,7 @@ extern "C" int v2v_brain_forward_backward(v2v_brain* b, const float* node, const
                 "reference's all-zero neighbour input");
     const int grid = tt_grid(*b->tt_plan, B);
     b->last_grid = grid;
-    if (int rc = tt_launch(*b->tt_plan, b->tt_plan_dev, P, b->tt_wimg, node, edge, im, om, y, nullptr, b->partial, B, 1, st)) return rc;
+    if (int rc = tt_launch(*b->tt_plan, b->tt_plan_dev, P, node, edge, im, y, nullptr, b->partial, B, 1, st)) return rc;
     if (b->defer_reduce) return 0;
     return fused_reduce_adam(b->partial, grid, tt_partial_stride((long)b->n_params), Gd, nullptr, nullptr, nullptr,
                              (long)b->n_params, N, hl, 0, 0.f, 0.f, 0.f, 0.f, 1.f, st);

@@ -14,6 +14,12 @@
 //     keeps the FP32-pipe kernel of fused.cu and this kernel is the bf16 configuration's).
 // The reference's concatenations ([h | node | edge | agg], :154-164; [node | h | agg], :175) are plane lists.
 //
+// The neighbour aggregation (AggLayer.call, :69-76) is a contraction as well once the tile's adjacency is written as
+// ONE block-diagonal 0/1 operand  adj[m][n]  (bf16, 16 planes, rebuilt per tile from the in_mask words: <= 4 sixteen-byte
+// entries per row):  agg = adj . h  reads it K-major with the h planes as the MN-major B operand, the backward
+// dh += adj^T . dagg  reads the SAME bytes MN-major and accumulates onto the dh columns the data-gradient MMA just
+// produced -- 0/1 times bf16 is exact, the sum is fp32 in TMEM.  No CUDA-core gather loop, no second mask orientation.
+//
 // Weight gradients never leave tensor memory during the kernel: three accumulator groups
 //   chain 1: [x0 | h0 | a0 | h1 | a1 | h2 | a2 | ..]^T  x  [dz0 | dz1 | dz2 | dm1 | dm2 | dm3 | dq]   (128 x 208 at S = 3)
 //   chain 2: [m1 | m2 | ..]^T x [dm2 | dm3],    chain 3: [m3 | ..]^T x [dq | 0]
@@ -22,10 +28,13 @@
 // product is ignored.  x0 carries a ones feature, so the bias gradients are row 15 of chain 1.  The per-CTA partials
 // (+ per-head Huber sums in the row tail) go through the same reduce + Keras-Adam kernel as the FP32 path (fused.cu).
 //
-// Rounding points (restated in oracle/bf16_emul.py): contraction operands are bf16 (RNE), accumulation is fp32 in
-// TMEM; bias, ReLU, the neighbour aggregation, the output layer and the Huber head are fp32; master weights, gradients
-// and Adam are fp32.  Warp roles: warp 16 issues MMAs from a per-tile table, 16 epilogue warps (4 TMEM lane quarters x
-// 4 column quarters) run the epilogues; one tile in flight, inputs of the next tile wait in registers.
+// Rounding points (restated in oracle/bf16_emul.py): contraction operands are bf16 (RNE) -- weights, inputs, h, agg, the
+// MLP activations, dq and every back-propagated dz / dagg -- accumulation is fp32 in TMEM; bias, ReLU, the output layer
+// and the Huber head are fp32; master weights, gradients and Adam are fp32.  Every CTA converts the fp32 master weights
+// into its bf16 image itself (35 KB read from L2 once per launch): no staging kernel, no global image.
+// Warp roles: warp 12 issues MMAs from a per-tile table, 12 epilogue warps (4 TMEM lane quarters x 3 column groups)
+// run the epilogues (TMEM -> registers -> bf16 planes, all lane-local); one tile in flight, the next tile's inputs wait
+// in registers.
 #include <algorithm>
 #include <vector>
 
@@ -88,80 +97,78 @@ __device__ __forceinline__ bool bf16_pos(uint32_t word, int half) {
   return h > 0;
 }
 
-// fp32 master weights -> bf16 weight image (k-planes of 8, see above) + fp32 bias image, once per call
-__global__ void __launch_bounds__(256)
-tt_stage_weights_kernel(const TtPlan* __restrict__ P, const float* __restrict__ params, __nv_bfloat16* __restrict__ wimg) {
-  asm volatile("griddepcontrol.wait;" ::: "memory");          // parameters may come from the preceding optimiser kernel
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  const int n_layers = P->n_layers;
-  float* bias_img = reinterpret_cast<float*>(wimg + P->w_elems);
-  for (int l = 0; l < n_layers; ++l) {
-    const TtLayerImg& L = P->layers[l];
-    const int Kpad = L.Kpad, Npad = L.Npad, No = L.No;
-    __nv_bfloat16* Wc = wimg + L.w_off;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < Kpad * Npad; idx += gridDim.x * blockDim.x) {
-      const int o = idx % Npad, k = idx / Npad;               // consecutive threads read consecutive o of one W row
-      const int wrow = L.kmap[k];
-      const float w = (wrow >= 0 && o < No) ? params[L.pw_off + wrow * No + o] : 0.f;
-      Wc[(k >> 3) * (Npad * 8) + o * 8 + (k & 7)] = __float2bfloat16_rn(w);
-    }
-    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < Npad; o += gridDim.x * blockDim.x)
-      bias_img[L.bias_off + o] = (o < No) ? params[L.pb_off + o] : 0.f;
-  }
-}
+// optional clock trace of CTA 0's first two tiles (profiling aid): per step 8 stamps
+//   [0] MMA thread: operands ready seen  [1] MMAs issued + committed
+//   [2] epilogue thread 0: accumulator ready seen  [3] TMEM loads back  [4] planes written  [5] fenced + arrived
+__device__ long long* g_tt_trace = nullptr;
 
 __global__ void __launch_bounds__(kTtThreads, 1)
-tt_kernel(const TtPlan* __restrict__ P, const uint8_t* __restrict__ wimg, const float* __restrict__ node,
-          const float* __restrict__ edge, const uint32_t* __restrict__ in_mask, const uint32_t* __restrict__ out_mask,
-          const float* __restrict__ y, float* __restrict__ q_out, float* __restrict__ partial, int B, int train, float inv_cnt) {
+tt_kernel(const TtPlan* __restrict__ P, const float* __restrict__ params, const float* __restrict__ node,
+          const float* __restrict__ edge, const uint32_t* __restrict__ in_mask, const float* __restrict__ y,
+          float* __restrict__ q_out, float* __restrict__ partial, int B, int train, float inv_cnt) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t ops_bar;          // operands of the next step are in place (16 warp arrivals)
   __shared__ __align__(8) uint64_t acc_bar;          // the step's accumulator is complete (tcgen05.commit)
   __shared__ __align__(8) uint64_t wg_bar;           // the tile's weight-gradient MMAs have consumed the planes
-  __shared__ __align__(8) uint64_t w_bar;            // the weight image has landed
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int N = P->N, TG = P->TG, Dn = P->Dn, De = P->De, CH = P->CH, F = P->F, XP = P->XP;
+  const int N = P->N, TG = P->TG, Dn = P->Dn, De = P->De, CH = P->CH, XP = P->XP;
   const int n_steps = train ? P->n_steps_train : P->n_steps_fwd;
   const int ones_f = P->ones_feature;
   float* bias_s = reinterpret_cast<float*>(smem + P->off_bias);
   uint8_t* planes = smem + P->off_planes;
-  float* scr = reinterpret_cast<float*>(smem + P->off_scr);          // fp32 scratch planes [c / 4][row][4]
-  uint32_t* mask_s = reinterpret_cast<uint32_t*>(smem + P->off_mask); // in_mask[128] | out_mask[128]
   float* hl_s = reinterpret_cast<float*>(smem + P->off_misc);        // per-head Huber sums [32]
   float* rowloss = hl_s + 32;                                        // [128]
-  TtMma* mma_s = reinterpret_cast<TtMma*>(smem + P->off_tab);
+  TtMmaRt* mma_s = reinterpret_cast<TtMmaRt*>(smem + P->off_tab);
   TtStep* step_s = reinterpret_cast<TtStep*>(mma_s + kTtMaxMma);
 
   if (tid == 0) {
     mbar_init(&ops_bar, kTtEpiThreads / 32);
     mbar_init(&acc_bar, 1);
     mbar_init(&wg_bar, 1);
-    mbar_init(&w_bar, 1);
     fence_mbar_init();
   }
   if (warp == 0) tt_tmem_alloc(&tmem_base_s, kTtTmemCols);
-  {                                                           // planes, scratch, masks, loss sums: finite everywhere
+  {                                                           // planes, loss sums: finite (zero) everywhere; tables
     uint32_t* z = reinterpret_cast<uint32_t*>(planes);
     const int nz = (P->off_tab - P->off_planes) / 4;
     for (int i = tid; i < nz; i += kTtThreads) z[i] = 0u;
-    const int n_mma_w = P->n_mma * (int)(sizeof(TtMma) / 4), n_step_w = kTtMaxSteps * (int)(sizeof(TtStep) / 4);
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(P->mma);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(mma_s);
-    for (int i = tid; i < n_mma_w; i += kTtThreads) dst[i] = src[i];
-    src = reinterpret_cast<const uint32_t*>(P->steps);
-    dst = reinterpret_cast<uint32_t*>(step_s);
+    const uint32_t sbase0 = smem_u32(smem);
+    for (int i = tid; i < P->n_mma; i += kTtThreads) {        // MMA table: descriptors ready to issue
+      const TtMma m = P->mma[i];
+      TtMmaRt r;
+      r.a_desc = tt_desc(sbase0 + m.a_off, m.a_lbo, m.a_sbo);
+      r.b_desc = tt_desc(sbase0 + m.b_off, m.b_lbo, m.b_sbo);
+      r.idesc = m.idesc; r.dcol = m.dcol; r.acc = m.acc; r.pad = 0u;
+      mma_s[i] = r;
+    }
+    const int n_step_w = kTtMaxSteps * (int)(sizeof(TtStep) / 4);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(P->steps);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(step_s);
     for (int i = tid; i < n_step_w; i += kTtThreads) dst[i] = src[i];
   }
-  __syncthreads();                                            // mbarrier inits and tables visible
-  asm volatile("griddepcontrol.wait;" ::: "memory");          // the weight image comes from tt_stage_weights_kernel
-  if (tid == 0) {
-    const uint32_t bytes = (uint32_t)(P->w_elems * 2 + P->bias_floats * 4);
-    mbar_arrive_expect_tx(&w_bar, bytes);
-    for (uint32_t off = 0; off < bytes; off += 32768u)
-      bulk_g2s(smem + P->off_w + off, wimg + off, min(32768u, bytes - off), &w_bar);
+  asm volatile("griddepcontrol.wait;" ::: "memory");          // the parameters come from the preceding optimiser kernel
+  // ---- fp32 master weights -> this CTA's bf16 image: entry (k-plane kp, output o) = 8 consecutive k of one o (16 bytes)
+  {
+    const int n_layers = P->n_layers;
+    for (int l = 0; l < n_layers; ++l) {
+      const TtLayerImg& L = P->layers[l];
+      const int Npad = L.Npad, No = L.No, entries = (L.Kpad >> 3) * Npad;
+      const float* Wp = params + L.pw_off;
+      uint8_t* img = smem + P->off_w + (size_t)L.w_off * 2;
+      for (int e = tid; e < entries; e += kTtThreads) {
+        const int kp = e / Npad, o = e - kp * Npad;           // consecutive threads read consecutive o of the same W rows
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int wrow = L.kmap[kp * 8 + j];
+          v[j] = (wrow >= 0 && o < No) ? __ldg(Wp + wrow * No + o) : 0.f;
+        }
+        *reinterpret_cast<uint4*>(img + (size_t)e * 16) = pack8(v);
+      }
+      for (int o = tid; o < Npad; o += kTtThreads) bias_s[L.bias_off + o] = (o < No) ? __ldg(params + L.pb_off + o) : 0.f;
+    }
   }
-  mbar_wait(&w_bar, 0u);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   fence_async_smem();
   tt_fence_before();
@@ -175,20 +182,43 @@ tt_kernel(const TtPlan* __restrict__ P, const uint8_t* __restrict__ wimg, const 
     if (lane == 0) {
       uint32_t po = 0u;
       bool first = true;
-      const uint32_t sbase = smem_u32(smem);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      long long* trace = (blockIdx.x == 0) ? g_tt_trace : nullptr;
+      int tile_i = 0;
+      // one MMA: the table entry is already in registers when the barrier opens (loaded before the wait / one entry ahead)
+      auto issue = [&](const uint4& lo, const uint4& hi) {
+        const uint64_t da = ((uint64_t)lo.y << 32) | lo.x, db = ((uint64_t)lo.w << 32) | lo.z;
+        const uint32_t acc = (hi.z == 0u) ? 0u : ((hi.z == 1u) ? 1u : (first ? 0u : 1u));
+        tt_mma_bf16(tmem_base + hi.y, da, db, hi.x, acc);
+      };
+      auto run = [&](int m0, int n) {                         // MMAs m0 .. m0 + n - 1, next entry prefetched during the issue
+        const uint4* tab = reinterpret_cast<const uint4*>(mma_s);
+        uint4 lo = tab[2 * m0], hi = tab[2 * m0 + 1];
+        for (int i = 0; i < n; ++i) {
+          const int nx = (i + 1 < n) ? m0 + i + 1 : m0;
+          const uint4 nlo = tab[2 * nx], nhi = tab[2 * nx + 1];
+          issue(lo, hi);
+          lo = nlo; hi = nhi;
+        }
+      };
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_i) {
         for (int s = 0; s < n_steps; ++s) {
+          const int m0 = step_s[s].mma0, n = step_s[s].n_mma, p0 = step_s[s].post0, np = step_s[s].n_post;
+          const int kind = step_s[s].kind;
+          const uint4* tab = reinterpret_cast<const uint4*>(mma_s);
+          uint4 lo = tab[2 * m0], hi = tab[2 * m0 + 1];       // first entry in registers before the barrier opens
           mbar_wait(&ops_bar, po);
           po ^= 1u;
           tt_fence_after();
-          const int m0 = step_s[s].mma0, m1 = m0 + step_s[s].n_mma;
-          for (int i = m0; i < m1; ++i) {
-            const TtMma m = mma_s[i];
-            const uint64_t da = tt_desc(sbase + m.a_off, m.a_lbo, m.a_sbo), db = tt_desc(sbase + m.b_off, m.b_lbo, m.b_sbo);
-            const uint32_t acc = (m.acc == 0u) ? 0u : ((m.acc == 1u) ? 1u : (first ? 0u : 1u));
-            tt_mma_bf16(tmem_base + m.dcol, da, db, m.idesc, acc);
+          if (trace && tile_i < 2) trace[(tile_i * kTtMaxSteps + s) * 8 + 0] = clock64();
+          for (int i = 0; i < n; ++i) {
+            const int nx = (i + 1 < n) ? m0 + i + 1 : m0;
+            const uint4 nlo = tab[2 * nx], nhi = tab[2 * nx + 1];
+            issue(lo, hi);
+            lo = nlo; hi = nhi;
           }
-          tt_commit(step_s[s].kind == TT_WGRAD ? &wg_bar : &acc_bar);
+          tt_commit(kind == TT_WGRAD ? &wg_bar : &acc_bar);
+          if (trace && tile_i < 2) trace[(tile_i * kTtMaxSteps + s) * 8 + 1] = clock64();
+          if (np > 0) run(p0, np);                            // weight-gradient chains: the tensor pipe runs them under the epilogue
         }
         first = false;
       }
@@ -199,17 +229,24 @@ tt_kernel(const TtPlan* __restrict__ P, const uint8_t* __restrict__ wimg, const 
     const int row = q4 * 32 + lane;                           // this thread's accumulator lane = tile row
     const uint32_t t_lane = tmem_base + ((uint32_t)(q4 * 32) << 16);
     uint32_t pa = 0u, pw = 0u;
-    // ---- input prefetch: the next tile's features / masks / targets wait in registers
+    // ---- this thread's entries of the block-diagonal adjacency operand: row m, k-planes kp0 + e, e = (tid >> 7) + kTtCQ i.
+    //      They do not depend on the tile (same graph positions every tile): only the mask word does.
+    const int am = tid & (kTtRows - 1);
+    const int ag = am / N;
+    const bool a_row = am < TG * N;
+    const int a_kp0 = (ag * N) >> 3, a_kp1 = (ag * N + N - 1) >> 3;
+    uint8_t* adj_planes = planes + (size_t)P->plane_adj * kTtPlaneBytes;
+    // ---- input prefetch: the next tile's features / mask word / targets wait in registers
     float xin[8], ynext[8];
     uint32_t mk = 0u;
     auto fetch = [&](int tile) {
       const int g0 = tile * TG;
       const int R = (tile < num_tiles) ? min(TG, B - g0) * N : 0;
-      const int r = tid & (kTtRows - 1), pl = tid >> 7;
+      const int pl = tid >> 7;
 #pragma unroll
       for (int j = 0; j < 8; ++j) { xin[j] = 0.f; ynext[j] = 0.f; }
-      if (pl < XP && r < R) {
-        const size_t gr = (size_t)g0 * N + r;
+      if (pl < XP && am < R) {
+        const size_t gr = (size_t)g0 * N + am;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int f = pl * 8 + j;
@@ -218,9 +255,7 @@ tt_kernel(const TtPlan* __restrict__ P, const uint8_t* __restrict__ wimg, const 
           else if (f == ones_f) xin[j] = 1.f;
         }
       }
-      mk = 0u;
-      if (tid < kTtRows) { if (tid < R) mk = __ldg(in_mask + (size_t)g0 * N + tid); }
-      else if (tid < 2 * kTtRows && train) { if (tid - kTtRows < R) mk = __ldg(out_mask + (size_t)g0 * N + (tid - kTtRows)); }
+      mk = (am < R) ? __ldg(in_mask + (size_t)g0 * N + am) : 0u;
       if (train && cq == 0 && row < R) {
         const float* yp = y + ((size_t)g0 * N + row) * CH;
 #pragma unroll
@@ -229,9 +264,12 @@ tt_kernel(const TtPlan* __restrict__ P, const uint8_t* __restrict__ wimg, const 
     };
     fetch(blockIdx.x);
     bool first = true;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    long long* trace = (blockIdx.x == 0 && tid == 0) ? g_tt_trace : nullptr;
+    int tile_i = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_i) {
       const int g0 = tile * TG;
       const int R = min(TG, B - g0) * N;
+      if (trace && tile_i < 2) trace[(tile_i * kTtMaxSteps + kTtMaxSteps - 1) * 8 + 6] = clock64();      // tile start
       if (train && !first) {                                  // the previous tile's weight-gradient MMAs still read the planes
         mbar_wait(&wg_bar, pw);
         pw ^= 1u;
@@ -239,9 +277,20 @@ tt_kernel(const TtPlan* __restrict__ P, const uint8_t* __restrict__ wimg, const 
       }
       first = false;
       {
-        const int r = tid & (kTtRows - 1), pl = tid >> 7;
-        if (pl < XP) *reinterpret_cast<uint4*>(planes + (size_t)pl * kTtPlaneBytes + r * 16) = pack8(xin);
-        if (tid < 2 * kTtRows) mask_s[tid] = mk;
+        const int pl = tid >> 7;
+        if (pl < XP) *reinterpret_cast<uint4*>(planes + (size_t)pl * kTtPlaneBytes + am * 16) = pack8(xin);
+        if (a_row) {
+          for (int kp = a_kp0 + pl; kp <= a_kp1; kp += kTtCQ) {
+            const int base = kp * 8 - ag * N;                 // source node of the entry's first element: in [-7, N)
+            const uint32_t bits = (base >= 0) ? (mk >> base) : (mk << (-base));
+            uint4 w;                                          // bit j -> bf16 1.0 (0x3F80) in element j
+            w.x = ((bits & 1u) ? 0x3F80u : 0u) | ((bits & 2u) ? 0x3F800000u : 0u);
+            w.y = ((bits & 4u) ? 0x3F80u : 0u) | ((bits & 8u) ? 0x3F800000u : 0u);
+            w.z = ((bits & 16u) ? 0x3F80u : 0u) | ((bits & 32u) ? 0x3F800000u : 0u);
+            w.w = ((bits & 64u) ? 0x3F80u : 0u) | ((bits & 128u) ? 0x3F800000u : 0u);
+            *reinterpret_cast<uint4*>(adj_planes + (size_t)kp * kTtPlaneBytes + am * 16) = w;
+          }
+        }
       }
       float ycur[8];
 #pragma unroll
@@ -258,56 +307,58 @@ tt_kernel(const TtPlan* __restrict__ P, const uint8_t* __restrict__ wimg, const 
         mbar_wait(&acc_bar, pa);
         pa ^= 1u;
         tt_fence_after();
-        const float* bs = bias_s + st.bias_off;
-        // ---- accumulator chunks of this thread: 8 columns each, chunk c8 = cq + 4 j
+        if (trace && tile_i < 2) trace[(tile_i * kTtMaxSteps + s) * 8 + 2] = clock64();
+        // ---- accumulator chunks of this thread: 8 columns each, chunk index = chunk0 + cq + 4 j
         uint32_t acc[4][8];
-        const int nch_ld = (st.kind == TT_DGRAD_AGG) ? (st.npad >> 3) : st.n_chunks;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int c8 = cq + 4 * j;
-          if (c8 < nch_ld) tt_ld8_issue(t_lane + (uint32_t)(c8 * 8), acc[j]);
+          const int c = cq + kTtCQ * j;
+          if (c < st.n_chunks) tt_ld8_issue(t_lane + (uint32_t)((st.chunk0 + c) * 8), acc[j]);
         }
         tt_wait_ld();
-        if (st.kind == TT_COMBINE || st.kind == TT_MLP) {
+        if (trace && tile_i < 2) trace[(tile_i * kTtMaxSteps + s) * 8 + 3] = clock64();
+        if (st.kind == TT_PLANES) {
+          // two chunks at a time: their shared-memory reads (bias vectors, gate planes) are issued before anything is consumed
+          const bool has_bias = st.bias_off >= 0, has_gate = st.gate_plane >= 0;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int c8 = cq + 4 * j;
-            if (c8 < nch_ld) {
-              float v[8];
+          for (int jp = 0; jp < 4; jp += 2) {
+            float4 b0[2], b1[2];
+            uint4 gt[2];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                v[i] = __uint_as_float(acc[j][i]) + bs[c8 * 8 + i];
-                if (st.relu) v[i] = fmaxf(v[i], 0.f);
-              }
-              if (st.kind == TT_COMBINE) {                    // fp32 copy for the aggregation
-                *reinterpret_cast<float4*>(scr + ((size_t)(2 * c8) * kTtRows + row) * 4) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(scr + ((size_t)(2 * c8 + 1) * kTtRows + row) * 4) = make_float4(v[4], v[5], v[6], v[7]);
-              }
-              *reinterpret_cast<uint4*>(planes + (size_t)(st.out_plane + c8) * kTtPlaneBytes + row * 16) = pack8(v);
-            }
-          }
-          if (st.kind == TT_COMBINE) {
-            // neighbour aggregation (AggLayer.call, :69-76): agg[g, m] = sum_n Adj[g][n][m] h[g, n], fp32, then bf16 planes
-            tt_epi_barrier();
-            const int items = (F >> 2) * TG * N;
-            for (int item = tid; item < items; item += kTtEpiThreads) {
-              const int m = item % N;                         // lanes of a warp share (feature quad, graph): broadcast reads
-              const int rest = item / N;
-              const int g = rest % TG, c4 = rest / TG;
-              const uint32_t k0 = mask_s[g * N + m];
-              const float* src = scr + ((size_t)c4 * kTtRows + g * N) * 4;
-              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-              for (int n = 0; n < N; ++n) {
-                if ((k0 >> n) & 1u) {
-                  const float4 t = *reinterpret_cast<const float4*>(src + n * 4);
-                  a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+            for (int jj = 0; jj < 2; ++jj) {
+              const int c = cq + kTtCQ * (jp + jj);
+              b0[jj] = b1[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+              gt[jj] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);       // "positive": no gate
+              if (c < st.n_chunks) {
+                if (has_bias) {
+                  const float4* bp = reinterpret_cast<const float4*>(bias_s + st.bias_off + (st.chunk0 + c) * 8);
+                  b0[jj] = bp[0]; b1[jj] = bp[1];
                 }
+                if (has_gate) gt[jj] = *reinterpret_cast<const uint4*>(planes + (size_t)(st.gate_plane + c) * kTtPlaneBytes + row * 16);
               }
-              *reinterpret_cast<uint2*>(planes + (size_t)(st.out2_plane + (c4 >> 1)) * kTtPlaneBytes + (g * N + m) * 16 + (c4 & 1) * 8) =
-                  make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
+            }
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              const int j = jp + jj, c = cq + kTtCQ * j;
+              if (c < st.n_chunks) {
+                float v[8];
+                v[0] = __uint_as_float(acc[j][0]) + b0[jj].x; v[1] = __uint_as_float(acc[j][1]) + b0[jj].y;
+                v[2] = __uint_as_float(acc[j][2]) + b0[jj].z; v[3] = __uint_as_float(acc[j][3]) + b0[jj].w;
+                v[4] = __uint_as_float(acc[j][4]) + b1[jj].x; v[5] = __uint_as_float(acc[j][5]) + b1[jj].y;
+                v[6] = __uint_as_float(acc[j][6]) + b1[jj].z; v[7] = __uint_as_float(acc[j][7]) + b1[jj].w;
+                if (st.relu) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                }
+                const uint32_t gw[4] = {gt[jj].x, gt[jj].y, gt[jj].z, gt[jj].w};   // relu'(saved activation): positive and non-zero
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = bf16_pos(gw[i >> 1], i & 1) ? v[i] : 0.f;
+                *reinterpret_cast<uint4*>(planes + (size_t)(st.out_plane + c) * kTtPlaneBytes + row * 16) = pack8(v);
+              }
             }
           }
-        } else if (st.kind == TT_Q) {
+        } else {   // TT_Q
+          const float* bs = bias_s + st.bias_off;
           if (train) {
             if (cq == 0) {
               float dq[8];
@@ -339,63 +390,15 @@ tt_kernel(const TtPlan* __restrict__ P, const uint8_t* __restrict__ wimg, const 
             for (int i = 0; i < 8; ++i)
               if (i < CH) qd[i] = __uint_as_float(acc[0][i]) + bs[i];
           }
-        } else if (st.kind == TT_DGRAD_MLP) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int c8 = cq + 4 * j;
-            if (c8 < nch_ld) {
-              const uint4 gt = *reinterpret_cast<const uint4*>(planes + (size_t)(st.gate_plane + c8) * kTtPlaneBytes + row * 16);
-              const uint32_t gw[4] = {gt.x, gt.y, gt.z, gt.w};
-              float v[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = bf16_pos(gw[i >> 1], i & 1) ? __uint_as_float(acc[j][i]) : 0.f;
-              *reinterpret_cast<uint4*>(planes + (size_t)(st.out_plane + c8) * kTtPlaneBytes + row * 16) = pack8(v);
-            }
-          }
-        } else {   // TT_DGRAD_AGG: accumulator = [dh (F) | dagg (F)] -> dz = gate * (dh + Agg^T dagg)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int c8 = cq + 4 * j;
-            if (c8 < nch_ld) {
-              *reinterpret_cast<float4*>(scr + ((size_t)(2 * c8) * kTtRows + row) * 4) =
-                  make_float4(__uint_as_float(acc[j][0]), __uint_as_float(acc[j][1]), __uint_as_float(acc[j][2]), __uint_as_float(acc[j][3]));
-              *reinterpret_cast<float4*>(scr + ((size_t)(2 * c8 + 1) * kTtRows + row) * 4) =
-                  make_float4(__uint_as_float(acc[j][4]), __uint_as_float(acc[j][5]), __uint_as_float(acc[j][6]), __uint_as_float(acc[j][7]));
-            }
-          }
-          tt_epi_barrier();
-          const int FQ = F >> 2;
-          const int items = FQ * TG * N;
-          const uint32_t* om = mask_s + kTtRows;
-          for (int item = tid; item < items; item += kTtEpiThreads) {
-            const int n = item % N;
-            const int rest = item / N;
-            const int g = rest % TG, c4 = rest / TG;
-            const int r = g * N + n;
-            const uint32_t k0 = om[r];                        // bit m = Adj[n][m]: whom n contributes to
-            float4 a = *reinterpret_cast<const float4*>(scr + ((size_t)c4 * kTtRows + r) * 4);
-            const float* src = scr + ((size_t)(FQ + c4) * kTtRows + g * N) * 4;
-            for (int m = 0; m < N; ++m) {
-              if ((k0 >> m) & 1u) {
-                const float4 t = *reinterpret_cast<const float4*>(src + m * 4);
-                a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
-              }
-            }
-            if (st.gate_plane >= 0) {
-              const uint2 gt = *reinterpret_cast<const uint2*>(planes + (size_t)(st.gate_plane + (c4 >> 1)) * kTtPlaneBytes + r * 16 + (c4 & 1) * 8);
-              a.x = bf16_pos(gt.x, 0) ? a.x : 0.f; a.y = bf16_pos(gt.x, 1) ? a.y : 0.f;
-              a.z = bf16_pos(gt.y, 0) ? a.z : 0.f; a.w = bf16_pos(gt.y, 1) ? a.w : 0.f;
-            }
-            *reinterpret_cast<uint2*>(planes + (size_t)(st.out_plane + (c4 >> 1)) * kTtPlaneBytes + r * 16 + (c4 & 1) * 8) =
-                make_uint2(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w));
-          }
         }
+        if (trace && tile_i < 2) trace[(tile_i * kTtMaxSteps + s) * 8 + 4] = clock64();
         if (s + 1 < n_steps) {                                // hand the next step's operands to the MMA warp
           fence_async_smem();
           tt_fence_before();
           __syncwarp();
           if (lane == 0) tt_mbar_arrive(&ops_bar);
         }
+        if (trace && tile_i < 2) trace[(tile_i * kTtMaxSteps + s) * 8 + 5] = clock64();
       }
     }
     if (train) {
@@ -411,7 +414,7 @@ tt_kernel(const TtPlan* __restrict__ P, const uint8_t* __restrict__ wimg, const 
         const TtBlock& blk = P->blocks[b];
         const int n = blk.n, nch = (n + 7) >> 3;
         const int d = blk.dst[row];
-        for (int c = cq; c < nch; c += 4) {
+        for (int c = cq; c < nch; c += kTtCQ) {
           uint32_t r8[8];
           tt_ld8_issue(t_lane + (uint32_t)(blk.tcol + c * 8), r8);
           tt_wait_ld();
@@ -442,8 +445,8 @@ int tt_build_plan(const TtShape& s, TtPlan* out) {
   V2V_REQUIRE(s.F == 16, "bf16 tensor-core brain: feedback width %d (needs 16)", s.F);
   V2V_REQUIRE(s.S >= 1 && s.S <= 3, "bf16 tensor-core brain: %d stages (supports 1..3)", s.S);
   V2V_REQUIRE(s.CH >= 1 && s.CH <= 8, "bf16 tensor-core brain: %d channels (supports <= 8)", s.CH);
-  V2V_REQUIRE(s.H1 >= 8 && s.H2 >= 8 && s.H3 >= 8 && s.H1 <= 128 && s.H2 <= 128 && s.H3 <= 128,
-              "bf16 tensor-core brain: hidden widths outside [8,128]");
+  V2V_REQUIRE(s.H1 >= 8 && s.H2 >= 8 && s.H3 >= 8 && s.H1 <= 32 * kTtCQ && s.H2 <= 32 * kTtCQ && s.H3 <= 32 * kTtCQ,
+              "bf16 tensor-core brain: hidden widths outside [8,%d]", 32 * kTtCQ);
   const int F = s.F, Dn = s.Dn, De = s.De, S = s.S, CH = s.CH;
   auto r16 = [](int v) { return (v + 15) & ~15; };
   auto planes_of = [](int v) { return (v + 7) / 8; };
@@ -506,15 +509,15 @@ int tt_build_plan(const TtShape& s, TtPlan* out) {
   }
   P.w_elems = w_elems;
   P.bias_floats = (bias_floats + 3) & ~3;
+  // ---- extra planes behind the gradients: the transient dagg planes, then the block-diagonal adjacency operand
+  const int pda = XT + DTp, padj = pda + FP, PT = padj + kTtRows / 8;
+  P.plane_adj = padj;
   // ---- shared memory carve-up
   int off = 0;
   auto take = [&](int bytes, int align) { off = (off + align - 1) & ~(align - 1); const int at = off; off += bytes; return at; };
   P.off_w = take(w_elems * 2, 128);
   P.off_bias = take(P.bias_floats * 4, 16);
-  V2V_REQUIRE(P.off_bias == P.off_w + w_elems * 2, "bf16 tensor-core brain: weight image not contiguous");
-  P.off_planes = take((XT + DTp) * kTtPlaneBytes, 128);
-  P.off_scr = take(2 * F / 4 * kTtRows * 16, 128);            // [dh | dagg] fp32: 2F columns
-  P.off_mask = take(2 * kTtRows * 4, 16);
+  P.off_planes = take(PT * kTtPlaneBytes, 128);
   P.off_misc = take((32 + kTtRows) * 4, 16);
   P.off_tab = take(kTtMaxMma * (int)sizeof(TtMma) + kTtMaxSteps * (int)sizeof(TtStep), 16);
   P.smem_bytes = off;
@@ -528,7 +531,13 @@ int tt_build_plan(const TtShape& s, TtPlan* out) {
            ((uint32_t)(kTtRows >> 4) << 24);
   };
   auto add_mma = [&](TtMma m) { if (n_mma >= kTtMaxMma) { overflow = true; return; } P.mma[n_mma++] = m; };
-  auto add_step = [&](TtStep st) { if (n_steps >= kTtMaxSteps) { overflow = true; return; } P.steps[n_steps++] = st; };
+  auto add_step = [&](int kind, int mma0, int chunk0, int n_chunks, int out_plane, int gate_plane, int bias_off, int relu) {
+    if (n_steps >= kTtMaxSteps) { overflow = true; return; }
+    TtStep& e = P.steps[n_steps++];
+    e = TtStep{};
+    e.kind = kind; e.mma0 = mma0; e.n_mma = n_mma - mma0; e.chunk0 = chunk0; e.n_chunks = n_chunks; e.out_plane = out_plane;
+    e.gate_plane = gate_plane; e.bias_off = bias_off; e.relu = relu;
+  };
   // forward contraction of layer l over a list of plane pairs
   auto fwd_mmas = [&](int l, const std::vector<int>& pair_first) {
     const TtLayerImg& L = P.layers[l];
@@ -540,7 +549,7 @@ int tt_build_plan(const TtShape& s, TtPlan* out) {
       add_mma(m);
     }
   };
-  // data gradient of layer l: dX[:, k-planes kp0 .. kp0 + nkp) = dZ (planes from dz_plane) . W^T
+  // data gradient of layer l: dX[:, k-planes kp0 .. kp0 + nkp) = dZ (planes from dz_plane) . W^T  (weights read MN-major)
   auto dgrad_mmas = [&](int l, int dz_plane, int kp0, int nkp) {
     const TtLayerImg& L = P.layers[l];
     const int ksteps = L.Npad / 16;
@@ -552,72 +561,83 @@ int tt_build_plan(const TtShape& s, TtPlan* out) {
       add_mma(m);
     }
   };
+  // neighbour aggregation over the tile's block-diagonal adjacency: D[:, 0:F) (+)= adj (or adj^T) . (planes from src)
+  auto agg_mmas = [&](int src_plane, bool transposed, bool accumulate) {
+    for (int ks = 0; ks < kTtRows / 16; ++ks) {
+      TtMma m{};
+      if (!transposed) { m.a_off = plane_off(padj + 2 * ks); m.a_lbo = kTtPlaneBytes; m.a_sbo = 128; }
+      else { m.a_off = plane_off(padj) + ks * 256; m.a_lbo = 128; m.a_sbo = kTtPlaneBytes; }
+      m.b_off = plane_off(src_plane) + ks * 256; m.b_lbo = 128; m.b_sbo = kTtPlaneBytes;
+      m.idesc = idesc(FP * 8, transposed ? 1 : 0, 1); m.dcol = 0; m.acc = (accumulate || ks > 0) ? 1u : 0u;
+      add_mma(m);
+    }
+  };
   auto pairs = [](int first, int count) { std::vector<int> v; for (int i = 0; i < count; i += 2) v.push_back(first + i); return v; };
   auto cat = [](std::vector<int> a, const std::vector<int>& b) { a.insert(a.end(), b.begin(), b.end()); return a; };
   for (int st = 0; st < S; ++st) {
-    TtStep e{};
-    e.kind = TT_COMBINE; e.mma0 = n_mma;
+    int m0 = n_mma;
     fwd_mmas(st, st == 0 ? pairs(px0, XP) : cat(cat(pairs(px0, XP), pairs(ph[st - 1], FP)), pairs(pa[st - 1], FP)));
-    e.n_mma = n_mma - e.mma0; e.npad = P.layers[st].Npad; e.n_chunks = FP; e.out_plane = ph[st]; e.out2_plane = pa[st];
-    e.gate_plane = -1; e.bias_off = P.layers[st].bias_off; e.relu = st < S - 1;
-    add_step(e);
+    add_step(TT_PLANES, m0, 0, FP, ph[st], -1, P.layers[st].bias_off, st < S - 1);       // h = act(combine + bias)
+    m0 = n_mma;
+    agg_mmas(ph[st], false, false);
+    add_step(TT_PLANES, m0, 0, FP, pa[st], -1, -1, 0);                                     // agg = adj . h
   }
   const int pm[3] = {pm1, pm2, pm3}, PM[3] = {P1, P2, P3};
   for (int j = 0; j < 4; ++j) {
     const int l = S + j;
-    TtStep e{};
-    e.kind = j < 3 ? TT_MLP : TT_Q; e.mma0 = n_mma;
+    const int m0 = n_mma;
     fwd_mmas(l, j == 0 ? cat(cat(pairs(px0, XP), pairs(ph[S - 1], FP)), pairs(pa[S - 1], FP)) : pairs(pm[j - 1], P.layers[l].Kpad / 8));
-    e.n_mma = n_mma - e.mma0; e.npad = P.layers[l].Npad;
-    e.n_chunks = j < 3 ? PM[j] : 1; e.out_plane = j < 3 ? pm[j] : pdq; e.out2_plane = -1; e.gate_plane = -1;
-    e.bias_off = P.layers[l].bias_off; e.relu = j < 3;
-    add_step(e);
+    if (j < 3) add_step(TT_PLANES, m0, 0, PM[j], pm[j], -1, P.layers[l].bias_off, 1);
+    else add_step(TT_Q, m0, 0, 1, pdq, -1, P.layers[l].bias_off, 0);
   }
   P.n_steps_fwd = n_steps;
   {
-    const int pdm[3] = {pdm1, pdm2, pdm3};
-    for (int j = 3; j >= 1; --j) {          // MLP layer S + j: dz = its output gradient, result = gated gradient of its input m_j
-      const int l = S + j;
-      TtStep e{};
-      e.kind = TT_DGRAD_MLP; e.mma0 = n_mma;
-      dgrad_mmas(l, j == 3 ? pdq : pdm[j], 0, P.layers[l].Kpad / 8);
-      e.n_mma = n_mma - e.mma0; e.npad = P.layers[l].Kpad; e.n_chunks = PM[j - 1]; e.out_plane = pdm[j - 1]; e.out2_plane = -1;
-      e.gate_plane = pm[j - 1]; e.bias_off = 0; e.relu = 0;
-      add_step(e);
-    }
-    {                                        // first MLP layer: [dh | dagg] of the last stage (linear: no gate)
-      TtStep e{};
-      e.kind = TT_DGRAD_AGG; e.mma0 = n_mma;
-      dgrad_mmas(S, pdm1, XP, 2 * FP);
-      e.n_mma = n_mma - e.mma0; e.npad = 2 * F; e.n_chunks = FP; e.out_plane = pdz[S - 1]; e.out2_plane = -1;
-      e.gate_plane = -1; e.bias_off = 0; e.relu = 0;
-      add_step(e);
-    }
-    for (int st = S - 1; st >= 1; --st) {    // stage st: [dh | dagg] of stage st - 1 (relu: gated by h(st - 1))
-      TtStep e{};
-      e.kind = TT_DGRAD_AGG; e.mma0 = n_mma;
-      dgrad_mmas(st, pdz[st], XP, 2 * FP);
-      e.n_mma = n_mma - e.mma0; e.npad = 2 * F; e.n_chunks = FP; e.out_plane = pdz[st - 1]; e.out2_plane = -1;
-      e.gate_plane = ph[st - 1]; e.bias_off = 0; e.relu = 0;
-      add_step(e);
-    }
-    // weight-gradient chains over the tile's 128 rows (8 k-steps of 16 rows), both operands MN-major
+    // weight-gradient chains over the tile's 128 rows (8 k-steps of 16 rows), both operands MN-major.  A chain is issued
+    // right after the commit of the step that consumes its last-produced dz operand, so the tensor pipe runs it while the
+    // epilogue warps work; only the chain of the GNN stages' dz (complete at the very end) is the tile's last step.
     const int nb2 = (P2 + P3 + 1) & ~1;
     const int tcol1 = kTtWorkCols, tcol2 = tcol1 + DTp * 8, tcol3 = tcol2 + nb2 * 8;
     V2V_REQUIRE(tcol3 + 16 <= (int)kTtTmemCols, "bf16 tensor-core brain: %d tensor-memory columns needed", tcol3 + 16);
-    TtStep e{};
-    e.kind = TT_WGRAD; e.mma0 = n_mma;
-    struct Chain { int a_plane, b_plane, nb, tcol; } chains[3] = {{px0, XT, DTp, tcol1}, {pm1, pdm2, nb2, tcol2}, {pm3, pdq, 2, tcol3}};
-    for (const Chain& c : chains)
+    auto wgrad_chain = [&](int a_plane, int b_plane, int nbp, int tcol) {
       for (int ks = 0; ks < kTtRows / 16; ++ks) {
         TtMma m{};
-        m.a_off = plane_off(c.a_plane) + ks * 256; m.a_lbo = 128; m.a_sbo = kTtPlaneBytes;
-        m.b_off = plane_off(c.b_plane) + ks * 256; m.b_lbo = 128; m.b_sbo = kTtPlaneBytes;
-        m.idesc = idesc(c.nb * 8, 1, 1); m.dcol = (uint32_t)c.tcol; m.acc = ks > 0 ? 1u : 2u;
+        m.a_off = plane_off(a_plane) + ks * 256; m.a_lbo = 128; m.a_sbo = kTtPlaneBytes;
+        m.b_off = plane_off(b_plane) + ks * 256; m.b_lbo = 128; m.b_sbo = kTtPlaneBytes;
+        m.idesc = idesc(nbp * 8, 1, 1); m.dcol = (uint32_t)tcol; m.acc = ks > 0 ? 1u : 2u;
         add_mma(m);
       }
-    e.n_mma = n_mma - e.mma0; e.gate_plane = -1; e.out_plane = e.out2_plane = -1;
-    add_step(e);
+    };
+    auto set_post = [&](int post0) { if (n_steps > 0) { P.steps[n_steps - 1].post0 = post0; P.steps[n_steps - 1].n_post = n_mma - post0; } };
+    const int pdm[3] = {pdm1, pdm2, pdm3};
+    for (int j = 3; j >= 1; --j) {          // MLP layer S + j: dz = its output gradient, result = gated gradient of its input m_j
+      const int l = S + j;
+      const int m0 = n_mma;
+      dgrad_mmas(l, j == 3 ? pdq : pdm[j], 0, P.layers[l].Kpad / 8);
+      add_step(TT_PLANES, m0, 0, PM[j - 1], pdm[j - 1], pm[j - 1], -1, 0);
+      const int p0 = n_mma;
+      if (j == 3) wgrad_chain(pm3, pdq, 2, tcol3);                                          // chain 3: [m3 ..]^T x [dq | 0]
+      if (j == 1) wgrad_chain(pm1, pdm2, nb2, tcol2);                                       // chain 2: [m1 | m2 ..]^T x [dm2 | dm3]
+      set_post(p0);
+    }
+    // layers that feed on [h | agg]: the first MLP layer (last stage is linear: no gate), then stages S-1 .. 1
+    for (int st = S; st >= 1; --st) {
+      int m0 = n_mma;
+      dgrad_mmas(st, st == S ? pdm1 : pdz[st], XP, 2 * FP);                                // accumulator = [dh | dagg]
+      add_step(TT_PLANES, m0, FP, FP, pda, -1, -1, 0);                                      // dagg -> bf16 planes
+      if (st == S) {                                                                         // chain 1a: [x0 | h | a ..]^T x [dm1 | dm2 | dm3 | dq | 0]
+        const int p0 = n_mma;
+        wgrad_chain(px0, pdm1, XT + DTp - pdm1, tcol1 + (pdm1 - XT) * 8);
+        set_post(p0);
+      }
+      m0 = n_mma;
+      agg_mmas(pda, true, true);                                                             // dh += adj^T . dagg
+      add_step(TT_PLANES, m0, 0, FP, pdz[st - 1], (st - 1 < S - 1) ? ph[st - 1] : -1, -1, 0);
+    }
+    {                                                                                        // chain 1b: [x0 | h | a ..]^T x [dz0 | .. | dz(S-1)]
+      const int m0 = n_mma;
+      wgrad_chain(px0, XT, FP * S, tcol1);
+      add_step(TT_WGRAD, m0, 0, 0, -1, -1, -1, 0);
+    }
     // ---- read-out table: which accumulator lane / column block is which parameter
     int nb = 0;
     auto new_block = [&](int tcol, int n) -> TtBlock* {
@@ -663,11 +683,15 @@ int tt_build_plan(const TtShape& s, TtPlan* out) {
   return 0;
 }
 
+int tt_set_trace(long long* dev_buf) {
+  V2V_CHECK_CUDA(cudaMemcpyToSymbol(g_tt_trace, &dev_buf, sizeof(dev_buf)));
+  return 0;
+}
+
 int tt_grid(const TtPlan& p, int B) { return std::max(1, std::min(ceil_div(B, p.TG), sm_count())); }
 
-int tt_launch(const TtPlan& ph, const TtPlan* plan_dev, const float* params, void* wimg, const float* node, const float* edge,
-              const uint32_t* in_mask, const uint32_t* out_mask, const float* y, float* q_out, float* partial_dev, int B,
-              int train, cudaStream_t st) {
+int tt_launch(const TtPlan& ph, const TtPlan* plan_dev, const float* params, const float* node, const float* edge,
+              const uint32_t* in_mask, const float* y, float* q_out, float* partial_dev, int B, int train, cudaStream_t st) {
   static int smem_set = 0;
   if (ph.smem_bytes > smem_set) {
     V2V_CHECK_CUDA(cudaFuncSetAttribute(tt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ph.smem_bytes));
@@ -676,16 +700,6 @@ int tt_launch(const TtPlan& ph, const TtPlan* plan_dev, const float* params, voi
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  {
-    cudaLaunchConfig_t ls{};
-    ls.gridDim = dim3(16);
-    ls.blockDim = dim3(256);
-    ls.stream = st;
-    ls.attrs = attr;
-    ls.numAttrs = 1;
-    V2V_CHECK_CUDA(cudaLaunchKernelEx(&ls, tt_stage_weights_kernel, plan_dev, params, reinterpret_cast<__nv_bfloat16*>(wimg)));
-    if (int rc = launch_status("tt_stage_weights_kernel")) return rc;
-  }
   cudaLaunchConfig_t lc{};
   lc.gridDim = dim3(tt_grid(ph, B));
   lc.blockDim = dim3(kTtThreads);
@@ -694,8 +708,7 @@ int tt_launch(const TtPlan& ph, const TtPlan* plan_dev, const float* params, voi
   lc.attrs = attr;
   lc.numAttrs = 1;
   const float inv_cnt = 1.f / ((float)B * (float)ph.CH);
-  V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, tt_kernel, plan_dev, (const uint8_t*)wimg, node, edge, in_mask, out_mask, y, q_out,
-                                    partial_dev, B, train, inv_cnt));
+  V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, tt_kernel, plan_dev, params, node, edge, in_mask, y, q_out, partial_dev, B, train, inv_cnt));
   return launch_status("tt_kernel");
 }
 

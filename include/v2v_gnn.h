@@ -186,6 +186,10 @@ int v2v_tc_plan(const v2v_brain_config* cfg, int* info8);
  * Host-only query: info8 = {capable, graphs per tile, steps per training tile, tcgen05.mma per training tile,
  * shared-memory bytes, operand planes, bf16 weight-image elements, weight-gradient column blocks}. */
 int v2v_tt_plan(const v2v_brain_config* cfg, int* info8);
+/* Profiling aid of that kernel: CTA 0 writes clock64() stamps of its first two tiles into dev_buf[(tile * 24 + step) * 8 + i]
+ * (i = 0 MMA thread saw the operands, 1 MMAs issued and committed, 2 epilogue saw the accumulator, 3 tensor-memory loads
+ * back, 4 planes written, 5 fenced and arrived; step 23 / i = 6: tile start).  dev_buf >= 2 * 24 * 8 entries; NULL disables. */
+int v2v_tt_set_trace(long long* dev_buf);
 /* debugging aid: tensor-core forward that also dumps the raw fp32 accumulator [128][Npad] of `layer` for the first tile */
 int v2v_brain_tc_debug(v2v_brain* b, const float* node_dev, const float* edge_dev, const uint32_t* in_mask_dev, int B,
                        int layer, float* q_dev, float* dbg_dev, int* npad_out, void* stream);

@@ -8,8 +8,9 @@ tightly (accumulation order and rounding-boundary flips only) in addition to the
 
   * operands of every contraction are bf16 (round-to-nearest-even): weights, inputs, activations, back-propagated
     gradients; products are exact, accumulation is fp32 on the device (fp64 here);
-  * bias add, ReLU, the neighbour aggregation (BS_brain.py:69-76), the Huber head (:86-87) and the output layer are fp32:
-    the aggregation sums the *unrounded* fp32 h rows, its result is then rounded for the next contraction;
+  * the neighbour aggregation (BS_brain.py:69-76) is one of those contractions (0/1 adjacency times bf16 rows): it sums
+    the ROUNDED h rows (forward) and the ROUNDED dagg rows (backward, accumulated onto the unrounded dh);
+  * bias add, ReLU, the Huber head (:86-87) and the output layer are fp32;
   * the weight gradient contracts the rounded activations with the rounded dz; the bias gradient sums the rounded dz;
   * master weights, gradients and Keras-Adam (:212) stay fp32 (not restated here: oracle/v2v_oracle.keras_adam_step).
 
@@ -50,13 +51,13 @@ def brain_forward_backward_bf16(dims: O.BrainDims, layers, node, edge, adj, y=No
     pre = x @ Wb[0][:Dn + De] + bias[0]
     h = O.relu(pre) if S > 1 else pre
     xs.append(x); pres.append(pre)
-    agg = O.agg_factored(f32(h), adj)
+    agg = O.agg_factored(bf16(h), adj)
     for s in range(1, S):
         x = np.concatenate([bf16(h), nb, eb, bf16(agg)], -1)
         pre = x @ Wb[s] + bias[s]
         h = O.relu(pre) if s < S - 1 else pre
         xs.append(x); pres.append(pre)
-        agg = O.agg_factored(f32(h), adj)
+        agg = O.agg_factored(bf16(h), adj)
     x = np.concatenate([nb, bf16(h), bf16(agg)], -1)
     nl = len(layers) - S
     for j in range(nl):
@@ -87,12 +88,12 @@ def brain_forward_backward_bf16(dims: O.BrainDims, layers, node, edge, adj, y=No
         if j > 0:
             dz = bf16(dx * (pres[li - 1] > 0))               # relu of the producing MLP layer
     # dx = d[node | h | agg] of the first MLP layer
-    dh = f32(dx[..., Dn:Dn + F]) + O.agg_factored_T(f32(dx[..., Dn + F:]), adj)
+    dh = f32(dx[..., Dn:Dn + F]) + O.agg_factored_T(bf16(dx[..., Dn + F:]), adj)
     for s in reversed(range(1, S)):
         dpre = bf16(dh * (pres[s] > 0) if s < S - 1 else dh)
         wgrad(s, xs[s], dpre)
         dx = dpre @ Wb[s].T                                  # d[h | node | edge | agg]
-        dh = f32(dx[..., :F]) + O.agg_factored_T(f32(dx[..., F + Dn + De:]), adj)
+        dh = f32(dx[..., :F]) + O.agg_factored_T(bf16(dx[..., F + Dn + De:]), adj)
     dpre = bf16(dh * (pres[0] > 0) if S > 1 else dh)
     wgrad(0, xs[0], dpre)
     return q_out, loss, per_head, grads

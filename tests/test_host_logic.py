@@ -104,9 +104,10 @@ def test_bf16_training_plan_host_query(v2v):
         assert lib.v2v_tt_plan(C.byref(_cfg(v2v, N, S)), info) == 0
         capable, tg, steps, mmas, smem, planes, wimg, blocks = list(info)
         assert capable == 1 and tg == 128 // N
-        assert steps == 2 * S + 8                      # S combine + 4 MLP forward, 3 MLP + S aggregated data gradients, 1 weight gradient
-        # forward k-steps of 16: 1, 3 per later stage, 3, 5, 3, 2; data gradient: 1, 2, 3, 5, 1 per later stage; weight gradient 3 x 8
-        assert mmas == (1 + 3 * (S - 1) + 3 + 5 + 3 + 2) + (1 + 2 + 3 + 5 + (S - 1)) + 24
+        assert steps == 4 * S + 8                      # per stage: combine + aggregate (forward), [dh|dagg] + transposed aggregate (backward); 4 MLP, 3 MLP data gradients, 1 weight gradient
+        # forward k-steps of 16: 1, 3 per later stage, 3, 5, 3, 2; data gradient: 1, 2, 3, 5, 1 per later stage; every
+        # aggregation is 8 k-steps over the tile's 128 rows (S forward, S backward); weight gradient 4 chains x 8 (three of them issued under the backward epilogues)
+        assert mmas == (1 + 3 * (S - 1) + 3 + 5 + 3 + 2) + (1 + 2 + 3 + 5 + (S - 1)) + 16 * S + 32
         assert smem <= 226 * 1024 and blocks == S + 7
         assert planes == (2 + 4 * S + 10 + 5 + 3) + (2 * S + 10 + 5 + 3 + 1 + (1 if (2 * S + 19) % 2 else 2))
         assert wimg == 16 * 16 + (S - 1) * 48 * 16 + 48 * 80 + 80 * 48 + 48 * 32 + 32 * 16

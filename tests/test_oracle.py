@@ -194,3 +194,40 @@ def test_huber_and_adam_against_independent_torch_implementations():
         (0.5 * pt @ torch.from_numpy(A) @ pt).backward()
         opt.step()
         np.testing.assert_allclose(p, pt.detach().numpy(), rtol=1e-9, atol=1e-12)
+
+
+def test_known_answers_literal_kronecker_form_and_identity_weights():
+    """Hand-derivable cases in the reference's LITERAL form: AggLayer.call as concat -> batch_dot against
+    kron(Adj, I_F) (BS_brain.py:69-76, :492-493) and GNNLayer.call (:44-51) with identity-like weights."""
+    N, F = 4, 16
+    # one-hot feature on node 2, Adj = 1 - I with node 0's own receiver (node 1) cleared as well (BS_brain.py:441-445)
+    adj = np.ones((N, N)) - np.eye(N)
+    adj[1, 0] = 0.0
+    A = O.kron_adjacency(adj, F)[None]
+    D = [np.zeros((1, F)) for _ in range(N)]
+    D[2][0, 5] = 1.0
+    out = O.agg_layer_call(D, A)
+    assert [o[0, 5] for o in out] == [1.0, 1.0, 0.0, 1.0] and sum(np.abs(o).sum() for o in out) == 3.0
+    D = [np.full((1, F), float(k + 1)) for k in range(N)]               # node k carries the constant k + 1
+    out = O.agg_layer_call(D, A)
+    assert [o[0, 0] for o in out] == [3.0 + 4.0, 1.0 + 3.0 + 4.0, 1.0 + 2.0 + 4.0, 1.0 + 2.0 + 3.0]   # column sums of adj
+    # GNNLayer with W1 = [I; 0], W2 = 0, W3 = I, bias = 1: out = a[:, :F] + c + 1 (linear) and relu of it
+    a = np.arange(25, dtype=np.float64)[None] - 12.0
+    b = np.ones((1, 4)); c = np.full((1, F), 0.5)
+    W1 = np.concatenate([np.eye(F), np.zeros((9, F))], 0)
+    lin = O.gnn_layer_call(a, b, c, W1, np.zeros((4, F)), np.eye(F), np.ones(F))
+    assert np.array_equal(lin, a[:, :F] + 1.5)
+    assert np.array_equal(O.gnn_layer_call(a, b, c, W1, np.zeros((4, F)), np.eye(F), np.ones(F), 'relu'), np.maximum(a[:, :F] + 1.5, 0))
+    # whole brain, all weights zero: Q = bias of the output layer; output weights = 1: Q = sum(relu(b3)) + b4
+    d = O.BrainDims(N, stages=3, per_slot=True)
+    L = [{'W': np.zeros((d.G, K, n)), 'b': np.zeros((d.G, n))} for K, n in d.layer_shapes()]
+    L[-1]['b'][:] = np.arange(4.0)
+    rng = np.random.default_rng(0)
+    node, edge, adjb, _ = O.synth_batch(3, N, rng)
+    assert np.array_equal(O.brain_forward(d, L, node, edge, adjb), np.broadcast_to(np.arange(4.0), (3, N, 4)))
+    L[-2]['b'][:] = np.linspace(-1.0, 1.0, 20)
+    L[-1]['W'][:] = 1.0
+    want = np.maximum(np.linspace(-1.0, 1.0, 20), 0).sum() + np.arange(4.0)
+    assert np.allclose(O.brain_forward(d, L, node, edge, adjb), want, rtol=0, atol=1e-12)
+    lit = O.brain_forward_literal(d, L, node, edge, O.kron_adjacency(adjb, F))
+    assert np.allclose(np.stack(lit, 1), want, rtol=0, atol=1e-12)
