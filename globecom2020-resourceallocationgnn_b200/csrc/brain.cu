@@ -84,7 +84,9 @@ struct v2v_brain {
   uint32_t* st_in_mask = nullptr; uint32_t* st_out_mask = nullptr;
   int* st_flag = nullptr;
   int* st_flag_host = nullptr;    // pinned
-  float* pin = nullptr;           // pinned staging of the *_views entry points: node | edge | neigh | adj | y | q | head losses
+  float* st_block = nullptr;      // ONE device block behind st_node .. st_out_mask, laid out like the pinned block below, so that
+                                  // small batches travel as a single H2D copy (node | edge | y | in_mask | out_mask are adjacent)
+  float* pin = nullptr;           // pinned staging of the *_views entry points, same offsets as st_block
   size_t pin_node = 0, pin_edge = 0, pin_neigh = 0, pin_adj = 0, pin_y = 0, pin_q = 0, pin_hl = 0, pin_im = 0, pin_om = 0;   // offsets (floats)
   // fused whole-network path (shared weights, N <= 32, binary adjacency)
   bool fused_capable = false;
@@ -171,8 +173,7 @@ extern "C" void v2v_brain_destroy(v2v_brain* b) {
   for (auto p : b->mlp) cudaFree(p);
   for (auto p : b->dmlp) cudaFree(p);
   cudaFree(b->dq); cudaFree(b->dh_a); cudaFree(b->dh_b); cudaFree(b->dagg); cudaFree(b->head_loss);
-  cudaFree(b->st_node); cudaFree(b->st_edge); cudaFree(b->st_neigh); cudaFree(b->st_adj); cudaFree(b->st_y); cudaFree(b->st_q);
-  cudaFree(b->st_in_mask); cudaFree(b->st_out_mask); cudaFree(b->st_flag);
+  cudaFree(b->st_block); cudaFree(b->st_flag);
   if (b->st_flag_host) cudaFreeHost(b->st_flag_host);
   if (b->pin) cudaFreeHost(b->pin);
   cudaFree(b->partial);
@@ -225,20 +226,25 @@ extern "C" int v2v_brain_create(const v2v_brain_config* cfg, v2v_brain** out) {
   rc |= dmalloc(&b->dq, rows * b->CH);
   rc |= dmalloc(&b->dh_a, rows * b->F); rc |= dmalloc(&b->dh_b, rows * b->F); rc |= dmalloc(&b->dagg, rows * b->F);
   rc |= dmalloc(&b->head_loss, b->N);
-  rc |= dmalloc(&b->st_node, rows * b->Dn); rc |= dmalloc(&b->st_edge, rows * b->De); rc |= dmalloc(&b->st_neigh, rows * b->F);
-  rc |= dmalloc(&b->st_adj, rows * b->N); rc |= dmalloc(&b->st_y, rows * b->CH); rc |= dmalloc(&b->st_q, rows * b->CH);
   const int W = ceil_div(b->N, 32);
-  if (cudaMalloc((void**)&b->st_in_mask, rows * W * 4) != cudaSuccess) rc = 1;
-  if (cudaMalloc((void**)&b->st_out_mask, rows * W * 4) != cudaSuccess) rc = 1;
   if (cudaMalloc((void**)&b->st_flag, sizeof(int)) != cudaSuccess) rc = 1;
   if (cudaMallocHost((void**)&b->st_flag_host, sizeof(int)) != cudaSuccess) rc = 1;
   {
+    // staging layout (floats), identical in the pinned block and in the device block: the tensors every call ships are
+    // adjacent (node | edge | y | in_mask | out_mask), the rarely shipped ones (neighbour input, dense adjacency) follow
     size_t o = 0;
     auto take = [&](size_t n) { const size_t at = o; o += (n + 63) & ~(size_t)63; return at; };
-    b->pin_node = take(rows * b->Dn); b->pin_edge = take(rows * b->De); b->pin_neigh = take(rows * b->F);
-    b->pin_adj = take(rows * b->N); b->pin_y = take(rows * b->CH); b->pin_q = take(rows * b->CH); b->pin_hl = take(b->N);
+    b->pin_node = take(rows * b->Dn); b->pin_edge = take(rows * b->De); b->pin_y = take(rows * b->CH);
     b->pin_im = take(rows * W); b->pin_om = take(rows * W);
+    b->pin_neigh = take(rows * b->F); b->pin_adj = take(rows * b->N); b->pin_q = take(rows * b->CH); b->pin_hl = take(b->N);
     if (cudaMallocHost((void**)&b->pin, o * sizeof(float)) != cudaSuccess) rc = 1;
+    if (cudaMalloc((void**)&b->st_block, o * sizeof(float)) != cudaSuccess) rc = 1;
+    if (!rc) {
+      b->st_node = b->st_block + b->pin_node; b->st_edge = b->st_block + b->pin_edge; b->st_y = b->st_block + b->pin_y;
+      b->st_in_mask = reinterpret_cast<uint32_t*>(b->st_block + b->pin_im);
+      b->st_out_mask = reinterpret_cast<uint32_t*>(b->st_block + b->pin_om);
+      b->st_neigh = b->st_block + b->pin_neigh; b->st_adj = b->st_block + b->pin_adj; b->st_q = b->st_block + b->pin_q;
+    }
   }
   if (rc) {
     std::string e = last_error();
@@ -768,8 +774,22 @@ static int stage_views(v2v_brain* b, const v2v_host_view* node, int n_node, cons
     t[n].mask_bytes = mask_bytes;
   }
   ++n;
+  // Small batches: every H2D copy costs ~5 us of driver time whatever its size, so the adjacent block node | edge | y |
+  // masks travels as ONE copy once all of it is staged; large batches keep one copy per tensor, issued the moment the
+  // tensor is complete (the copy of the features overlaps the bit-packing of the adjacency).
+  const size_t merged_floats = b->pin_om + (size_t)rows * ceil_div(b->N, 32) - b->pin_node;
+  const bool merge = host_pack && merged_floats * sizeof(float) <= 512 * 1024;
+  if (merge) {
+    for (int i = 0; i < n; ++i)
+      if (i != i_neigh) { t[i].device = nullptr; t[i].dev_in_mask = nullptr; t[i].dev_out_mask = nullptr; }
+  }
   int flags[kHostStageMaxTensors] = {0};
   if (int rc = host_stage_run(t, n, st, flags)) return rc;
+  if (merge) {
+    V2V_CHECK_CUDA(cudaMemcpyAsync(b->st_block + b->pin_node, b->pin + b->pin_node, merged_floats * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (flags[i_adj] & kFlagNonbinary)           // weighted adjacency: the dense matrix was staged into the pinned block by the fallback
+      V2V_CHECK_CUDA(cudaMemcpyAsync(b->st_adj, b->pin + b->pin_adj, (size_t)rows * b->N * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
   *weighted = (flags[i_adj] & kFlagNonbinary) != 0;
   *has_neigh = i_neigh >= 0 && (flags[i_neigh] & kFlagNonzero) != 0;
   if (!*weighted && !host_pack)

@@ -244,15 +244,16 @@ template <bool SLOT>
 __device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* arena, const float* Ws, const int* tab, int RP,
                                           int zero_row, int tid, const int (&my_blk)[kFusedBlkPerThread],
                                           float (&wacc)[kFusedBlkPerThread][16], int my_bias, float& bacc, float* dWs,
-                                          int* dx_ctr, int G, int TGp, float* part) {
+                                          int* dx_ctr, int G, int TGp, float* part, bool first_tile) {
   // ---- weight gradient.  Large layers: 4x4 blocks owned by fixed threads, accumulated in registers across
   // tiles.  Small layers (op.nwt = RS > 0): every block is split over RS adjacent lanes by row groups, reduced
   // with shuffles, and the first lane adds the block into the CTA's shared accumulator (one owner per
   // address: deterministic) -- otherwise a 5..48-block layer would leave most of the CTA idle.
   int owners_begin = 0, owners_n = 0;
   if (SLOT) {
-    // per-slot weights: block (slot, kb, ob) sums over the TGp rows of its slot and is added straight into this CTA's
-    // partial row in global memory (one owner per address and tile: deterministic; the row was zeroed in the prologue)
+    // per-slot weights: block (slot, kb, ob) sums over the TGp rows of its slot and goes straight into this CTA's partial
+    // row in global memory (one owner per address and tile: deterministic).  The CTA's first tile stores (nothing to
+    // read, nothing to zero beforehand), later tiles load all 16 values, add, store: no dependent round trips.
     const int OB = op.O >> 2, KB = (op.K + 3) >> 2;
     const int per_slot = KB * OB;
     for (int blk = tid; blk < G * per_slot; blk += kFusedThreads) {
@@ -262,13 +263,21 @@ __device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* 
 #pragma unroll
       for (int i = 0; i < 16; ++i) a[i] = 0.f;
       wgrad_block(op, arena, tab, RP, zero_row, kb, ob, slot * TGp, 4, (slot + 1) * TGp, a);
-      float* dst = part + op.w_off + slot * op.slot_w;
+      float* dst = part + op.w_off + slot * op.slot_w + (kb * 4) * op.O + ob;
+      if (!first_tile) {
+        float old[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) old[i * 4 + j] = (kb * 4 + i < op.K) ? __ldcg(dst + i * op.O + j * OB) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] += old[i];
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int k = kb * 4 + i;
-        if (k < op.K) {
+        if (kb * 4 + i < op.K) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dst[k * op.O + ob + j * OB] += a[i * 4 + j];
+          for (int j = 0; j < 4; ++j) dst[i * op.O + j * OB] = a[i * 4 + j];
         }
       }
     }
@@ -280,7 +289,15 @@ __device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* 
         const float4 t = *reinterpret_cast<const float4*>(dz + r);
         sb += (t.x + t.y) + (t.z + t.w);
       }
-      part[op.b_off + slot * op.slot_b + o] += sb;
+      float* bd = part + op.b_off + slot * op.slot_b + o;
+      *bd = first_tile ? sb : (__ldcg(bd) + sb);
+    }
+    if (first_tile) {                                        // parameter rows without an input (stage-0 neighbour rows): exact zeros
+      const int Kp = op.slot_w / op.O, dead = (Kp - op.K) * op.O;
+      for (int idx = tid; idx < G * dead; idx += kFusedThreads) {
+        const int slot = idx / dead, r = idx - slot * dead;
+        part[op.w_off + slot * op.slot_w + op.K * op.O + r] = 0.f;
+      }
     }
   } else if (op.nwt > 0) {
     const int RS = op.nwt, OB = op.O >> 2;
@@ -415,7 +432,14 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
   uint32_t* mask_s = reinterpret_cast<uint32_t*>(ops + n_ops);
   float* hl_s = reinterpret_cast<float*>(mask_s + ((2 * TG * N + 3) & ~3));
   float* dWs = hl_s + 32;                                   // shared weight-gradient accumulator of the small layers
-  float* arena = dWs + P->n_small;
+  float* wbuf = dWs + P->n_small;                           // per-slot weights: two layer buffers filled by bulk-async copies
+  const int wstage = SLOT ? P->wstage_floats : 0;
+  float* arena = wbuf + 2 * wstage;
+  __shared__ __align__(8) uint64_t wbar[2];
+  if (SLOT && tid == 0) {
+    mbar_init(&wbar[0], 1); mbar_init(&wbar[1], 1);
+    fence_mbar_init();
+  }
   float* part = (train && partial) ? partial + (size_t)blockIdx.x * (n_params + kFusedPartialTail) : nullptr;
 
   // programmatic dependent launch: everything up to griddepcontrol.wait overlaps the tail of the preceding kernel
@@ -436,8 +460,6 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
     for (int i = tid; i < n_params / 4; i += kFusedThreads)
       reinterpret_cast<float4*>(Ws_s)[i] = reinterpret_cast<const float4*>(params)[i];
     for (int i = (n_params & ~3) + tid; i < n_params; i += kFusedThreads) Ws_s[i] = params[i];
-  } else if (train) {
-    for (int i = tid; i < n_params; i += kFusedThreads) part[i] = 0.f;   // weight-gradient blocks are added tile by tile
   }
 
   // the whole grid is resident (one CTA per SM): let the dependent reduce/Adam kernel be scheduled now, its CTAs
@@ -458,6 +480,26 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
   float bacc = 0.f;
 
   const int n_tiles = (B + TG - 1) / TG;
+  // per-slot weights: the layers' [W | bias] spans stream through two shared-memory buffers, one layer ahead of its use
+  int wcur = 0;
+  uint32_t wpar[2] = {0u, 0u};
+  auto next_weight_op = [&](int from) {
+    for (int o2 = from; o2 < n_ops; ++o2)
+      if (ops[o2].type == FOP_GEMM || ops[o2].type == FOP_BWD) return o2;
+    return -1;
+  };
+  auto issue_weights = [&](int o2, int buf) {               // one thread
+    const uint32_t bytes = (uint32_t)ops[o2].w_span * 4u;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(params + ops[o2].w_off);
+    uint8_t* dstb = reinterpret_cast<uint8_t*>(wbuf + (size_t)buf * wstage);
+    mbar_arrive_expect_tx(&wbar[buf], bytes);
+    for (uint32_t off = 0; off < bytes; off += 32768u) bulk_g2s(dstb + off, src + off, min(32768u, bytes - off), &wbar[buf]);
+  };
+  __syncthreads();                           // ops / barriers visible before the first prefetch
+  if (SLOT && wstage > 0 && tid == 0 && blockIdx.x < n_tiles) {
+    const int o2 = next_weight_op(0);
+    if (o2 >= 0) issue_weights(o2, 0);
+  }
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int g0 = tile * TG;
     const int ng = min(TG, B - g0);
@@ -514,17 +556,29 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
     for (int oi = 0; oi < n_ops; ++oi) {
       const FusedOp& op = ops[oi];
       if (tid == 0) dx_ctr[(oi + 1) & 1] = 0;              // the NEXT phase's work queue (idle: its last user ended a barrier ago)
+      const float* Wop = Ws;
+      if (SLOT && wstage > 0 && (op.type == FOP_GEMM || op.type == FOP_BWD)) {
+        mbar_wait(&wbar[wcur], wpar[wcur]);                // this layer's span has landed
+        wpar[wcur] ^= 1u;
+        if (tid == 0) {                                    // the other buffer's last reader ended a barrier ago: refill it
+          int nx = next_weight_op(oi + 1);
+          if (nx < 0 && tile + (int)gridDim.x < n_tiles) nx = next_weight_op(0);
+          if (nx >= 0) issue_weights(nx, wcur ^ 1);
+        }
+        Wop = wbuf + (size_t)wcur * wstage - op.w_off;      // so that Wop + op.w_off (+ slot strides) and Wop + op.b_off index the span
+        wcur ^= 1;
+      }
       switch (op.type) {
         case FOP_GEMM: {
           const int rg4 = RP / 4;
-          if (op.O % 8 == 0 && rg4 * (op.O / 8) >= (kFusedThreads * 3) / 4) gemm_phase<4, 8, SLOT>(op, arena, Ws, tab, RP, TGp, tid);
-          else if (SLOT || rg4 * (op.O / 4) >= kFusedThreads / 2) gemm_phase<4, 4, SLOT>(op, arena, Ws, tab, RP, TGp, tid);
-          else gemm_phase<2, 4, SLOT>(op, arena, Ws, tab, RP, TGp, tid);
+          if (op.O % 8 == 0 && rg4 * (op.O / 8) >= (kFusedThreads * 3) / 4) gemm_phase<4, 8, SLOT>(op, arena, Wop, tab, RP, TGp, tid);
+          else if (SLOT || rg4 * (op.O / 4) >= kFusedThreads / 2) gemm_phase<4, 4, SLOT>(op, arena, Wop, tab, RP, TGp, tid);
+          else gemm_phase<2, 4, SLOT>(op, arena, Wop, tab, RP, TGp, tid);
           break;
         }
         case FOP_AGG: agg_phase<NMAX, SLOT>(op, arena, tab, mask_s, RP, N, TG, TGp, tid); break;
         case FOP_LOSS: loss_phase<SLOT>(P, arena, tab, hl_s, RP, ng, inv_cnt, tid); break;
-        case FOP_BWD: bwd_phase<SLOT>(op, oi, arena, Ws, tab, RP, P->zero_row, tid, my_blk, wacc, my_bias, bacc, dWs, &dx_ctr[oi & 1], G, TGp, part); break;
+        case FOP_BWD: bwd_phase<SLOT>(op, oi, arena, Wop, tab, RP, P->zero_row, tid, my_blk, wacc, my_bias, bacc, dWs, &dx_ctr[oi & 1], G, TGp, part, tile == (int)blockIdx.x); break;
         default: break;
       }
       if (trace) trace[((oi + 1) * kFusedWarps + warp) * 2] = clock64();
@@ -709,6 +763,7 @@ int fused_build_program(const FusedShape& s, int TG, int train, FusedProgram* ou
     g->type = FOP_GEMM; g->in_tab = b.tab_put(gemm_in[st]); g->K = (int)gemm_in[st].size();
     g->out_tab = b.tab_put(h[st]); g->O = F; g->w_off = (int)s.w_off[st]; g->b_off = (int)s.b_off[st];
     g->slot_w = s.layer_K[st] * s.layer_O[st]; g->slot_b = s.layer_O[st];
+    g->w_span = s.G * (g->slot_w + g->slot_b);
     g->relu = st < S - 1;
     FusedOp* ag = b.add_op();
     ag->type = FOP_AGG; ag->in_tab = b.tab_put(h[st]); ag->K = F; ag->out_tab = b.tab_put(a[st]); ag->O = F;
@@ -724,6 +779,7 @@ int fused_build_program(const FusedShape& s, int TG, int train, FusedProgram* ou
     g->type = FOP_GEMM; g->in_tab = b.tab_put(gemm_in[l]); g->K = (int)gemm_in[l].size();
     g->out_tab = b.tab_put(mrows[j]); g->O = widths[j]; g->w_off = (int)s.w_off[l]; g->b_off = (int)s.b_off[l];
     g->slot_w = s.layer_K[l] * s.layer_O[l]; g->slot_b = s.layer_O[l];
+    g->w_span = s.G * (g->slot_w + g->slot_b);
     g->relu = j < 3;
   }
   P->q_tab = b.tab_put(mrows[3]);
@@ -750,6 +806,7 @@ int fused_build_program(const FusedShape& s, int TG, int train, FusedProgram* ou
       o->in_tab = b.tab_put(gemm_in[l]); o->K = (int)gemm_in[l].size();
       o->O = s.layer_O[l]; o->w_off = (int)s.w_off[l]; o->b_off = (int)s.b_off[l];
       o->slot_w = s.layer_K[l] * s.layer_O[l]; o->slot_b = s.layer_O[l];
+      o->w_span = s.G * (o->slot_w + o->slot_b);
       o->dz_tab = b.tab_put(dz);
       o->n_dx = (int)dxk.size();
       if (o->n_dx) { o->dxk_tab = b.tab_put(dxk); o->dx_tab = b.tab_put(dx); }
@@ -822,6 +879,15 @@ int fused_build_program(const FusedShape& s, int TG, int train, FusedProgram* ou
     P->n_bias = bias;
   }
   P->n_rows = b.next_row;
+  if (slot) {          // stream the weights through shared memory when two buffers of the largest layer span fit beside a useful arena
+    int span = 0;
+    for (int l = 0; l < s.n_layers; ++l) {
+      V2V_REQUIRE(s.b_off[l] == s.w_off[l] + (size_t)s.G * s.layer_K[l] * s.layer_O[l], "fused path: a layer's bias must follow its weights");
+      span = std::max(span, s.G * (s.layer_K[l] * s.layer_O[l] + s.layer_O[l]));
+    }
+    span = (span + 3) & ~3;
+    P->wstage_floats = (2 * span * 4 <= 112 * 1024) ? span : 0;
+  }
   V2V_REQUIRE(!b.overflow, "fused path: program tables overflow");
   return 0;
 }
@@ -834,6 +900,7 @@ size_t fused_smem_bytes(const FusedProgram& p) {
   words += (2 * p.TG * p.N + 3) & ~3;
   words += 32;
   words += p.n_small;
+  words += 2 * (size_t)p.wstage_floats;
   words += (size_t)p.n_rows * p.RP;
   return words * 4;
 }

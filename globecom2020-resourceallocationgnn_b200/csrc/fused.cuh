@@ -30,7 +30,8 @@ struct FusedOp {
   int wt0, nwt;           // BWD: nwt = RS > 0 marks a small layer (blocks split over RS lanes by rows), wt0 = its offset in
                           // the shared accumulator dWs
   int slot_w, slot_b;     // per-slot weights (G == N): floats between the W / bias of consecutive node slots
-  int pad_[2];            // (sizeof(FusedOp) stays a multiple of 16 bytes: shared-memory carve-up alignment)
+  int w_span;             // per-slot weights: floats of the layer's contiguous [W[G][K][O] | bias[G][O]] span (staged by TMA)
+  int pad_;               // (sizeof(FusedOp) stays a multiple of 16 bytes: shared-memory carve-up alignment)
 };
 static_assert(sizeof(FusedOp) % 16 == 0, "FusedOp must stay 16-byte sized");
 
@@ -57,6 +58,8 @@ struct FusedProgram {
   // (G == N, the reference's model, BS_brain.py:121-200): slot-major, row n * TGp + g with TGp = TG rounded up to 4, so
   // that the 4 rows of a register tile always share one weight set.
   int G, TGp, row_g, row_n;
+  int wstage_floats;      // per-slot weights: floats of ONE of the two shared-memory weight buffers the layers' spans are
+                          // streamed through (bulk-async copies, one layer ahead); 0: read the weights from global memory
   FusedOp ops[kFusedMaxOps];
   int tab[kFusedMaxTab];
   // block b -> op index, k0, o0 (packed: op<<16 | k0<<8 | o0), bias slot -> op<<16 | o

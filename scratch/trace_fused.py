@@ -2,9 +2,9 @@ import sys, numpy as np, torch, ctypes as C
 sys.path.insert(0,'/root/repo')
 import v2v_gnn_b200 as v2v
 from bench import synth_numpy
-N,S,B=20,int(sys.argv[1]) if len(sys.argv)>1 else 2,int(sys.argv[2]) if len(sys.argv)>2 else 1024
+N=int(sys.argv[3]) if len(sys.argv)>3 else 20; PS=len(sys.argv)>4 and sys.argv[4]=="slot"; S=int(sys.argv[1]) if len(sys.argv)>1 else 2; B=int(sys.argv[2]) if len(sys.argv)>2 else 1024
 rng=np.random.default_rng(0)
-brain=v2v.BS(N,3,1,16,1,4,stages=S,per_slot=False,max_batch=B,data_parallel=False,seed=1)
+brain=v2v.BS(N,3,1,16,1,4,stages=S,per_slot=PS,max_batch=B,data_parallel=False,seed=1)
 print(brain.fused_info(B,True))
 node,edge,adj=synth_numpy(B,N,rng)
 nd,ed,ad=(torch.from_numpy(t.astype(np.float32)).cuda() for t in (node,edge,adj))

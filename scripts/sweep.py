@@ -64,8 +64,8 @@ def agg_point(B, N, dtype=torch.float32, sparse=0):
     return set_bytes, us_dep, us_ind
 
 
-def brain_point(B, N, S=2):
-    brain = v2v.BS(N, 3, 1, 16, 1, 4, stages=S, per_slot=False, max_batch=B, data_parallel=False, seed=1)
+def brain_point(B, N, S=2, dtype="f32", per_slot=False):
+    brain = v2v.BS(N, 3, 1, 16, 1, 4, stages=S, per_slot=per_slot, max_batch=B, data_parallel=False, seed=1, dtype=dtype)
     rng = np.random.default_rng(B + N)
     node, edge, adj = synth_numpy(B, N, rng)
     nd, ed, ad = (torch.from_numpy(t).cuda() for t in (node, edge, adj))
@@ -121,6 +121,19 @@ def main():
                 continue
             us, info = brain_point(B, N)
             path = f"fused, {info['graphs_per_tile']} graphs/tile" if info["capable"] else "layer-by-layer kernels"
+            print(f"{N:4d} {B:6d} {us:9.1f} {B / us * 1e6:12.0f}  {path}", flush=True)
+    print("\n# brain fwd + Huber + bwd + Adam, BASELINE configs[2] form: 3 stages, shared weights, bf16 operands on tcgen05 (csrc/tc_train.cu)")
+    print(f"{'N':>4} {'B':>6} {'us/step':>9} {'graphs/s':>12}  path")
+    for N in (8, 20, 32):
+        for B in ((1024, 8192) if quick else (256, 1024, 4096, 8192, 32768)):
+            us, _ = brain_point(B, N, S=3, dtype="bf16")
+            print(f"{N:4d} {B:6d} {us:9.1f} {B / us * 1e6:12.0f}  tcgen05 bf16, {128 // N} graphs/tile", flush=True)
+    print("\n# the reference's own model: per-slot weights, 3 stages, fp32 (fused one-launch kernel up to N = 8)")
+    print(f"{'N':>4} {'B':>6} {'us/step':>9} {'graphs/s':>12}  path")
+    for N in (4, 8):
+        for B in ((256, 4096) if quick else (1, 64, 256, 512, 4096, 32768)):
+            us, info = brain_point(B, N, S=3, per_slot=True)
+            path = f"fused per-slot, {info['graphs_per_tile']} graphs/tile" if info["capable"] else "layer-by-layer kernels"
             print(f"{N:4d} {B:6d} {us:9.1f} {B / us * 1e6:12.0f}  {path}", flush=True)
 
 

@@ -75,6 +75,27 @@ def main():
             assert abs(lh - hs.history["loss"][0]) < 1e-4 * abs(hs.history["loss"][0]), (lh, hs.history["loss"][0])
     # the peer path carries the per-head losses through the same exchange: global mean on every rank
     assert np.abs(results["peer"][2] - sl).max() < 1e-4 * np.abs(sl).max()
+    # the bf16 tensor-core configuration (3 stages) through the same fused exchange: ranks' shards vs the full batch
+    os.environ["V2V_DP_BACKEND"] = "peer"
+    d3 = O.BrainDims(N, stages=3, per_slot=False)
+    p3 = O.flatten_params(O.init_params(d3, np.random.default_rng(11), bias_scale=0.05)).astype(np.float32)
+    bd = v2v.BS(N, 3, 1, 16, 1, 4, stages=3, per_slot=False, max_batch=Bl * world, data_parallel=True, seed=1, dtype="bf16")
+    bs = v2v.BS(N, 3, 1, 16, 1, 4, stages=3, per_slot=False, max_batch=Bl * world, data_parallel=False, seed=1, dtype="bf16")
+    bd.set_flat_params(p3, 0); bs.set_flat_params(p3, 0)
+    im_l, om_l, _ = v2v.pack_adjacency(dev(adj[lo:hi]))
+    q_full = bs.forward_device(dev(node), dev(edge), in_mask=im)
+    y3 = (q_full + 0.4).contiguous()
+    for _ in range(2):
+        l_dp = bd.train_step_device(dev(node[lo:hi]), dev(edge[lo:hi]), im_l, om_l, None, y3[lo:hi].contiguous())
+        l_sp = bs.train_step_device(dev(node), dev(edge), im, om, None, y3)
+    v2v._lib.check(bd._lib.v2v_comm_check(bd._comm, v2v._lib.current_stream()))
+    g_dp, g_sp = bd.get_flat_params(2), bs.get_flat_params(2)
+    assert np.abs(g_dp - g_sp).max() <= 2e-3 * np.abs(g_sp).max(), np.abs(g_dp - g_sp).max() / np.abs(g_sp).max()
+    assert np.abs(l_dp.cpu().numpy() - l_sp.cpu().numpy()).max() <= 1e-4 * np.abs(l_sp.cpu().numpy()).max()
+    mine = torch.from_numpy(bd.get_flat_params(0)).cuda()
+    ref = mine.clone()
+    dist.broadcast(ref, src=0)
+    assert torch.equal(mine, ref), "bf16: replicas diverged"
     dist.barrier()
     if rank == 0:
         print("DP_WORKER_OK world", world)
