@@ -34,3 +34,7 @@ for f in ("bench_n1", "bench_ref", "bench_c3_weak_n1", "bench_c3_strong_n1", "be
         print(f, "ERR", repr(e))
 PY
 ls -la $O | tail -12
+# memcheck of the round-2 kernels on small cases (bf16 tcgen05 training kernel, per-slot fused kernel)
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_bf16.py tests/test_gpu_brain.py -m gpu -q \
+  -k "test_bf16_train_step and 7-1-50 or test_bf16_forward and 2-2-9 or test_fused_kernel_matches_layered_kernels and 4-3-5-True" \
+  > $O/sanitizer_$TAG.log 2>&1; echo "memcheck rc=$?"; tail -4 $O/sanitizer_$TAG.log
