@@ -670,10 +670,38 @@ def run_c4(a, v2v, lib, dev):
 
 
 def cpu_baseline_bounded(a):
-    """~10-30 s of host work: the reference-form step on a bounded sample of the same workload."""
-    return {k: v for k, v in cpu_reference_run(a, None, 3, budget_s=12.0,
-                                               note="oracle port timed on the GPU box's host cores").items()
-            if k in ("value", "unit", "cores", "kind", "sample")}
+    """~10-30 s of host work: the reference-form step on a bounded sample of the same workload, and -- the fairer CPU line
+    BASELINE.md section 3 promises -- the factored-form step (adjacency as (B,N,N), packed layers) on the same sample."""
+    res = cpu_reference_run(a, None, 3, budget_s=12.0, note="oracle port timed on the GPU box's host cores")
+    out = {k: v for k, v in res.items() if k in ("value", "unit", "cores", "kind", "sample")}
+    out["median_ms_per_step"] = res["median_ms_per_step"]
+    try:
+        out["factored_form"] = cpu_factored_run(a, res["graphs_per_step"], budget_s=6.0)
+    except Exception as e:                                    # the reported baseline is the reference-form line above
+        out["factored_form"] = {"error": repr(e)}
+    return out
+
+
+def cpu_factored_run(a, bs, budget_s):
+    """Same fit step with the aggregation in factored form (einsum over the (B,N,N) adjacency instead of the bmm against the
+    dense Kronecker operand) and packed [B,N,.] layer calls: what a CPU implementation free of the reference's form costs."""
+    import torch
+    from oracle import v2v_oracle as O
+    from oracle import torch_ref as T
+    rng = np.random.default_rng(SEED)
+    d = O.BrainDims(a.nodes, stages=a.stages, per_slot=bool(a.per_slot))
+    model = T.ReferenceFormCPU(d, O.init_params(d, rng), dtype=torch.float32, form="factored")
+    node, edge, adj = synth_numpy(bs, a.nodes, rng, a.sparse)
+    y = rng.normal(0, 1, (bs, a.nodes, d.CH)).astype(np.float32)
+    data = [torch.from_numpy(t) for t in (node, edge, adj, y)]
+    for _ in range(3):
+        model.fit_step(*data)
+    times, t_start = [], time.perf_counter()
+    while len(times) < 30 or (time.perf_counter() - t_start < budget_s and len(times) < 300):
+        t0 = time.perf_counter(); model.fit_step(*data); times.append(time.perf_counter() - t0)
+    return {"value": bs / float(np.median(times)), "unit": "graphs/s", "median_ms_per_step": 1e3 * float(np.median(times)),
+            "min_ms_per_step": 1e3 * float(np.min(times)), "steps": len(times), "graphs_per_step": bs,
+            "cores": int(torch.get_num_threads()), "kind": "port (factored form)"}
 
 
 # --------------------------------------------------------------------------- batched-environment CPU leg

@@ -175,4 +175,4 @@ class ReferenceFormCPU:
         self.t += 1
         grads = [t.grad if t.grad is not None else torch.zeros_like(t) for t in self.flat]
         keras_adam_(self.flat, grads, self.m, self.v, self.t)
-        return float(loss), per_head.detach()
+        return float(loss.detach()), per_head.detach()
