@@ -23,10 +23,12 @@
 // Weight gradients never leave tensor memory during the kernel: three accumulator groups
 //   chain 1: [x0 | h0 | a0 | h1 | a1 | h2 | a2 | ..]^T  x  [dz0 | dz1 | dz2 | dm1 | dm2 | dm3 | dq]   (128 x 208 at S = 3)
 //   chain 2: [m1 | m2 | ..]^T x [dm2 | dm3],    chain 3: [m3 | ..]^T x [dq | 0]
-// are accumulated over ALL tiles of the CTA (24 MMAs per tile) and read out once, at the end, into the CTA's partial
-// row; the wanted blocks (layer l: inputs of l x dz of l) are picked by a lane / column table, the rest of the cross
-// product is ignored.  x0 carries a ones feature, so the bias gradients are row 15 of chain 1.  The per-CTA partials
-// (+ per-head Huber sums in the row tail) go through the same reduce + Keras-Adam kernel as the FP32 path (fused.cu).
+// are accumulated over ALL tiles of the CTA and read out once, at the end, into the CTA's partial row; the wanted blocks
+// (layer l: inputs of l x dz of l) are picked by a lane / column table, the rest of the cross product is ignored.  x0
+// carries a ones feature, so the bias gradients are row 15 of chain 1.  Chain 1 is issued in two column ranges (the MLP's
+// dz columns as soon as dm1 exists, the stages' dz columns at the very end): 32 MMAs per tile, 24 of them issued right
+// after the commit of a backward step, so that the tensor pipe runs them under that step's epilogue.  The per-CTA
+// partials (+ per-head Huber sums in the row tail) go through the same reduce + Keras-Adam kernel as the FP32 path.
 //
 // Rounding points (restated in oracle/bf16_emul.py): contraction operands are bf16 (RNE) -- weights, inputs, h, agg, the
 // MLP activations, dq and every back-propagated dz / dagg -- accumulation is fp32 in TMEM; bias, ReLU, the output layer
