@@ -18,6 +18,8 @@
 //     LDS.128 each) and adds the row into the accumulators whose mask bit is set
 //     (predicated packed FADD2), i.e. a register-tiled gather-reduce.
 // Generic path: any N <= 256 / F, one thread per output element.
+#include <type_traits>
+
 #include "agg_kernels.cuh"
 
 namespace v2v {
@@ -120,15 +122,31 @@ static int agg_block_min_n() {      // tunable for experiments: V2V_AGG_BLOCK_MI
   return v;
 }
 
-template <typename T, int MT, int MP, int NC = 0>
+// 8 < N <= 20: dense predicated gather-reduce, or the set-bit / clear-bit walk against the graph's column total.
+// Measured (profiles/agg_variants_r02.txt): with fp32 storage the kernel is bandwidth-bound and the walk buys nothing (it
+// lengthens the per-tile latency and costs ~1e-6 of parity), with bf16 storage the bytes halve, the predicated adds bind
+// (0.49 of the roofline) and the walk's 24 % fewer instructions pay; the stored result is rounded to bf16 either way.
+// V2V_AGG_WALK=0 / 1 forces one form for both storage types (experiments).
+template <typename T>
+static bool agg_use_walk() {
+  static int v = -2;
+  if (v == -2) {
+    const char* e = getenv("V2V_AGG_WALK");
+    v = e ? atoi(e) : -1;
+  }
+  if (v >= 0) return v != 0;
+  return std::is_same<T, __nv_bfloat16>::value;
+}
+
+template <typename T, int MT, int MP, int NC = 0, bool WALK = false>
 static int launch_fast(const T* H, const uint32_t* mask, const T* addend, T* out, int B, int N, bool independent,
                        cudaStream_t st) {
   constexpr int TG = 32 / (4 * MP);
   AggLaunchCfg cfg;
   cfg.dep_wait = !independent;
   cfg.ctas_per_sm = agg_fast_fits<T>(N, TG, addend != nullptr, kAggWarps, 2) ? 2 : 1;
-  if (addend) return launch_agg_fast<T, MT, MP, true, kAggWarps, true, NC>(H, mask, addend, out, B, N, cfg, st);
-  return launch_agg_fast<T, MT, MP, false, kAggWarps, true, NC>(H, mask, addend, out, B, N, cfg, st);
+  if (addend) return launch_agg_fast<T, MT, MP, true, kAggWarps, true, NC, WALK>(H, mask, addend, out, B, N, cfg, st);
+  return launch_agg_fast<T, MT, MP, false, kAggWarps, true, NC, WALK>(H, mask, addend, out, B, N, cfg, st);
 }
 
 template <typename T>
@@ -139,9 +157,13 @@ static int agg_mask_dispatch(const T* H, const uint32_t* mask, const T* addend, 
   if (F == 16 && N <= 20 && aligned && B > 0) {
     // small graphs: dense predicated gather-reduce (profiles/agg_variants_r01.txt)
     if (N <= 8 && agg_fast_fits<T>(N, 8, add, kAggWarps, 1)) return launch_fast<T, 8, 1>(H, mask, addend, out, B, N, independent, st);
+    const bool walk = agg_use_walk<T>();
     if (N == 20 && agg_fast_fits<T>(N, 2, add, kAggWarps, 1))       // the north-star shape: compile-time N
-      return launch_fast<T, 5, 4, 20>(H, mask, addend, out, B, N, independent, st);
-    if (agg_fast_fits<T>(N, 2, add, kAggWarps, 1)) return launch_fast<T, 5, 4>(H, mask, addend, out, B, N, independent, st);
+      return walk ? launch_fast<T, 5, 4, 20, true>(H, mask, addend, out, B, N, independent, st)
+                  : launch_fast<T, 5, 4, 20>(H, mask, addend, out, B, N, independent, st);
+    if (agg_fast_fits<T>(N, 2, add, kAggWarps, 1))
+      return walk ? launch_fast<T, 5, 4, 0, true>(H, mask, addend, out, B, N, independent, st)
+                  : launch_fast<T, 5, 4>(H, mask, addend, out, B, N, independent, st);
   }
   if (F == 16 && N <= 256 && aligned && B > 0) {
     // larger graphs: set-bit / clear-bit walk (work ~ N * min(deg, N - deg)); one warp per graph tile up to

@@ -126,3 +126,20 @@ def test_fused_plan_per_slot_host_query(v2v):
     assert capable == 1 and 1 <= tg <= 64 and smem <= 226 * 1024 and blocks == 0 and bias_slots == 0
     assert lib.v2v_fused_plan(C.byref(_cfg(v2v, 4, 3, per_slot=0)), 256, 1, info) == 0 and info[5] > 0
     assert lib.v2v_fused_plan(C.byref(_cfg(v2v, 20, 3, per_slot=1)), 256, 1, info) == 0 and info[0] == 0     # per-slot beyond N = 8: layered
+
+
+def test_bench_config_is_identical_in_both_arms(monkeypatch):
+    """bench.py: the engine arm and the reference arm describe the workload with the SAME `config` object (the driver
+    compares them), and --config c3 selects BASELINE configs[2] (3 stages, bf16; strong scaling = 8192 graphs in total)."""
+    import sys
+    import bench
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", "8", "--config", "c3", "--scaling", "strong"])
+    a = bench.parse()
+    assert (a.stages, a.dtype, a.batch) == (3, "bf16", 8192) and bench.per_gpu_batch(a, 8) == 1024
+    cfg = bench.config_dict(a, 8)
+    assert cfg["global_batch"] == 8192 and cfg["graphs_per_gpu"] == 1024 and cfg["parallelism"] == "dp8"
+    monkeypatch.setattr(sys, "argv", ["bench.py"])
+    a = bench.parse()
+    assert (a.config, a.stages, a.dtype, a.batch, a.scaling) == ("c2", 2, "f32", 1024, "weak")
+    c1 = bench.config_dict(a, 1)
+    assert c1 == bench.config_dict(a, 1) and "configs[1]" in c1["workload"] and c1["edges_per_graph"] == 360
