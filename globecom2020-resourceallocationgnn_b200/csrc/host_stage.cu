@@ -295,7 +295,7 @@ int host_stage_run(const HostStageTensor* tensors, int n_tensors, cudaStream_t s
       h2d(T.dev_out_mask, T.pin_out_mask, T.mask_bytes);
       continue;                        // the dense matrix was not staged: see below
     }
-    if (T.copy_if == 0 || (f & T.copy_if)) h2d(T.device, T.pinned, T.bytes);
+    if (T.copy_if == 0 || (f & T.copy_if)) h2d(T.device, T.h2d_from ? T.h2d_from : T.pinned, T.bytes);
   }
   while (job->active.load(std::memory_order_acquire) > 0) StagePool::cpu_relax();
   // weighted adjacency (values outside {0,1}; never produced by the reference, :441-445): the kernels need the dense

@@ -15,6 +15,7 @@ struct HostStageTensor {
   float* pinned;         // destination (pinned host memory)
   float* device;         // H2D target (nullptr: stage only)
   size_t bytes;          // bytes to copy to the device once all views have landed
+  const float* h2d_from; // source of that copy (nullptr: `pinned`); lets the last of several adjacent tensors ship all of them at once
   int check;             // 0, kCheckBinary (values outside {0,1}?) or kCheckNonzero (any non-zero value?)
   int copy_if;           // 0: always copy to the device; else only if (flags & copy_if)
   // adjacency tensors [B][N][N] with N <= 32: the workers also build the bit masks (adj_pack_kernel's job) in pinned
