@@ -34,6 +34,21 @@ MAX_EPSILON = 1                    # :276
 MIN_EPSILON = 0.01                 # :277
 
 
+def td_targets_device(lib, p, p_next, action, reward, gamma):
+    """DQN target rule (BS_brain.py:668-692) on device tensors: y = p except y[b, k, a[b, k]] = r[b] + gamma * max p_next[b, k].
+    The C entry point takes raw pointers, so dtype / layout / shape are checked here."""
+    B, N, CH = p.shape
+    for name, t, dt, shape in (("p", p, torch.float32, (B, N, CH)), ("p_next", p_next, torch.float32, (B, N, CH)),
+                               ("action", action, torch.int32, (B, N)), ("reward", reward, torch.float32, (B,))):
+        if not t.is_cuda or t.dtype != dt or not t.is_contiguous() or tuple(t.shape) != shape:
+            raise ValueError(f"td_targets_device: {name} must be a contiguous CUDA {dt} tensor of shape {shape}, got "
+                             f"{t.dtype} {tuple(t.shape)}")
+    y = torch.empty_like(p)
+    _lib.check(lib.v2v_td_target(ptr(p), ptr(p_next), ptr(action), ptr(reward), float(gamma), ptr(y), B, N, CH,
+                                 _lib.current_stream()))
+    return y
+
+
 class ReplayRing:
     """Replay memory stored as ( s, a, r, s_ ) in packed tensors (replaces BS_brain.py:245-270).
 
@@ -90,6 +105,12 @@ class ReplayRing:
             return
         if T > self.capacity:
             raise ValueError("more transitions than the ring holds")
+        for name, t, ref in (("node", node, self.node), ("edge", edge, self.edge), ("node_", node_, self.node_),
+                             ("edge_", edge_, self.edge_), ("in_mask", in_mask, self.in_mask), ("out_mask", out_mask, self.out_mask),
+                             ("reward", reward, self.reward)):
+            if t.device != ref.device or t.dtype != ref.dtype or t.numel() != T * ref[0].numel():
+                raise ValueError(f"ReplayRing.add_device: {name} must be {ref.dtype} on {ref.device} with {T} x "
+                                 f"{tuple(ref.shape[1:])} elements, got {t.dtype} {tuple(t.shape)} on {t.device}")
         idx = (self.head + torch.arange(T, device=self.device)) % self.capacity
         for dst, src in ((self.node, node), (self.edge, edge), (self.node_, node_), (self.edge_, edge_), (self.in_mask, in_mask),
                          (self.out_mask, out_mask), (self.action, action.to(torch.int32)), (self.reward, reward)):
@@ -219,9 +240,7 @@ class Agent:
         brain = self.brain
         p = brain.forward_device(batch["node"], batch["edge"], in_mask=batch["in_mask"])                      # :664
         p_ = brain.forward_device(batch["node_"], batch["edge_"], in_mask=batch["in_mask"], target=True)       # :665
-        y = torch.empty_like(p)
-        _lib.check(self._lib.v2v_td_target(ptr(p), ptr(p_), ptr(batch["action"]), ptr(batch["reward"]), float(self.gamma),
-                                           ptr(y), B, N, CH, _lib.current_stream()))                          # :668-692
+        y = td_targets_device(self._lib, p, p_, batch["action"], batch["reward"], self.gamma)                  # :668-692
         losses = brain.train_step_device(batch["node"], batch["edge"], batch["in_mask"], batch["out_mask"], None, y)  # :728
         stats = torch.stack([y.mean(dim=(0, 2)), y.max(dim=2).values.mean(dim=0),
                              p.mean(dim=(0, 2)), p.max(dim=2).values.mean(dim=0), losses]).cpu().numpy()          # :731-746
@@ -355,9 +374,7 @@ class BatchedAgent:
         brain = self.brain
         p = brain.forward_device(node, edge, in_mask=im)                                    # :664
         p_ = brain.forward_device(node_, edge_, in_mask=im, target=True)                    # :665
-        y = torch.empty_like(p)
-        _lib.check(self._lib.v2v_td_target(ptr(p), ptr(p_), ptr(action), ptr(reward), float(self.gamma), ptr(y), B, N, CH,
-                                           _lib.current_stream()))                          # :668-692
+        y = td_targets_device(self._lib, p, p_, action, reward, self.gamma)                 # :668-692
         losses = brain.train_step_device(node, edge, im, om, None, y)                       # :728
         return losses, y.mean(dim=(0, 2)), p.mean(dim=(0, 2))
 
