@@ -6,7 +6,7 @@ This image has neither package (no cp312 wheel, no network), which is why oracle
 Run this script on any machine that has them (Python 3.6/3.7):
 
     pip install keras==2.2.4 tensorflow==1.14.0 numpy
-    python scripts/make_tf1_golden.py --reference /path/to/Globecom2020-ResourceAllocationGNN --out tests/golden
+    python tests/golden/make_tf1_golden.py --reference /path/to/Globecom2020-ResourceAllocationGNN --out tests/golden
 
 It imports the reference's own `BS` class (BS_brain.py:90-239, nothing re-implemented), injects seeded weights layer by
 layer, feeds seeded inputs in the reference's dict format (BS_brain.py:495-504: per-slot arrays + kron(Adj, I_F)) and
@@ -26,7 +26,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import v2v_oracle as O      # noqa: E402  (NumPy only: dimensions and the flat parameter layout)
 

@@ -1,4 +1,4 @@
-"""Real-reference pins: vectors written by scripts/make_tf1_golden.py from the UNMODIFIED BS_brain.py under Keras 2.2.4 /
+"""Real-reference pins: vectors written by tests/golden/make_tf1_golden.py from the UNMODIFIED BS_brain.py under Keras 2.2.4 /
 TensorFlow 1.14.0.  That stack cannot be installed in this image, so the files are produced elsewhere and
 dropped into tests/golden/tf1_*.npz; until they exist these tests skip and the brain oracle stays "parity unpinned".
 When they exist: the NumPy oracle (CPU) and the CUDA engine (GPU) must both reproduce the reference's predict, loss and
@@ -13,7 +13,7 @@ from conftest import GOLDEN
 from oracle import v2v_oracle as O
 
 FILES = sorted(glob.glob(os.path.join(GOLDEN, "tf1_*.npz")))
-needs_files = pytest.mark.skipif(not FILES, reason="no tests/golden/tf1_*.npz (run scripts/make_tf1_golden.py where Keras 2.2.4 / "
+needs_files = pytest.mark.skipif(not FILES, reason="no tests/golden/tf1_*.npz (run tests/golden/make_tf1_golden.py where Keras 2.2.4 / "
                                                    "TF 1.14 exist)")
 
 

@@ -1,6 +1,6 @@
 import os, sys, ctypes as C
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT)
 import v2v_gnn_b200 as v2v
 from oracle import v2v_oracle as O
 np.set_printoptions(precision=4, suppress=True, linewidth=200)

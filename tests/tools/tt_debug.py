@@ -1,7 +1,7 @@
 """bf16 tensor-core brain against oracle/bf16_emul.py: where do the deviations sit? (scratch; a checker like tests/)"""
 import os, sys
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT)
 import v2v_gnn_b200 as v2v
 from oracle import v2v_oracle as O, bf16_emul as E
 N, S, B = (int(x) for x in (sys.argv[1:4] if len(sys.argv) > 3 else (20, 3, 64)))
