@@ -242,8 +242,11 @@ class Agent:
         p_ = brain.forward_device(batch["node_"], batch["edge_"], in_mask=batch["in_mask"], target=True)       # :665
         y = td_targets_device(self._lib, p, p_, batch["action"], batch["reward"], self.gamma)                  # :668-692
         losses = brain.train_step_device(batch["node"], batch["edge"], batch["in_mask"], batch["out_mask"], None, y)  # :728
+        # The reference writes the TD value INTO the array predict returned (`t = p[D][b]; t[a] = ...`, :683-690), so by the
+        # time it computes its "Orig_Q" statistics (:742-746) p equals the targets: all four statistics are statistics of
+        # y.  Reproduced as executed (recording of the unmodified Agent: tests/test_refshim_agent.py).
         stats = torch.stack([y.mean(dim=(0, 2)), y.max(dim=2).values.mean(dim=0),
-                             p.mean(dim=(0, 2)), p.max(dim=2).values.mean(dim=0), losses]).cpu().numpy()          # :731-746
+                             y.mean(dim=(0, 2)), y.max(dim=2).values.mean(dim=0), losses]).cpu().numpy()          # :731-746
         hist = History()
         hist.history = {"loss": [float(stats[4].sum())]}
         for k in range(N):

@@ -7,14 +7,24 @@ here).  It is the *checker* for the CUDA path.  Only ``tests/``,
 ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
 reference`` legs may import it; the product package never does.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or trained
-weights and its runtime (Keras/TF1) cannot run in this image,
-so the layer arithmetic below restates the *published* semantics of the pinned
-Keras/TF versions at the reference's own call sites.  What *is* pinned against
-code that runs here: the adjacency/feature packing, checked against the
-unmodified ``Environment.py`` (tests/golden/make_golden.py), and the
-manual backward, checked against an independent torch-autograd restatement
-(oracle/torch_ref.py) in fp64.
+PARITY: the reference ships no tests, golden vectors or trained weights
+ and its runtime (Keras 2.2.4 / TF 1.14) cannot run in this
+image, so byte-for-byte TF1 output is NOT available: against real TensorFlow
+this oracle is still "parity unpinned" (tests/golden/make_tf1_golden.py is the
+committed recipe that closes it wherever that stack exists).  What it IS pinned
+to, by code that runs here:
+ * the reference's OWN model code -- the unmodified ``BS_brain.py`` (GNNLayer,
+   AggLayer, BS._create_model, train_dnn, predict, Agent.replay,
+   Agent.generate_d2d_transition) executed on tests/keras_shim, a stand-in that
+   restates only the Keras/TF primitives it calls; recordings in
+   tests/golden/refshim_*.npz, checks in tests/test_tf1_golden.py and
+   tests/test_refshim_agent.py.  Every wiring decision (what is concatenated
+   with what, which layers are shared, the TD rule as executed) is therefore
+   the reference's, not a reading of it;
+ * the adjacency/feature packing: the unmodified ``Environment.py``
+   (tests/golden/make_golden.py);
+ * the manual backward: an independent torch-autograd restatement
+   (oracle/torch_ref.py) in fp64.
 
 Every function cites the reference lines it follows.  All math is dtype-generic
 (pass fp64 arrays for the high-precision oracle, fp32 for like-for-like).

@@ -18,7 +18,7 @@ def pytest_configure(config):
 # parallel) run before the "next" rows (f: DQN loop, batched environment), so that under `-x` a failure in an f-row
 # can never hide the parity tests of the judged kernels.
 _ORDER = ["test_capi_symbols", "test_oracle", "test_host_stage", "test_host_logic", "test_gpu_kernels", "test_gpu_layers",
-          "test_gpu_brain", "test_gpu_bf16", "test_gpu_tc", "test_gpu_dp", "test_gpu_dqn", "test_dqn_host", "test_env_oracle",
+          "test_gpu_brain", "test_tf1_golden", "test_refshim_agent", "test_gpu_bf16", "test_gpu_tc", "test_gpu_dp", "test_gpu_dqn", "test_dqn_host", "test_env_oracle",
           "test_gpu_env"]
 
 
@@ -31,7 +31,8 @@ def pytest_collection_modifyitems(session, config, items):
 
 def golden_cases():
     # brain cases only: the simulator recordings (sim_*.npz, tests/golden/make_env_golden.py) have their own tests
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith("sim_"))
+    # and so have the vectors recorded from the reference's own model code (refshim_*/tf1_*.npz, tests/test_tf1_golden.py)
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith(("sim_", "refshim_", "tf1_")))
 
 
 @pytest.fixture(scope="session")

@@ -21,6 +21,7 @@ the output layers are named D{k}_Decide_Output.  Shapes are asserted.
 """
 import argparse
 import os
+import random
 import re
 import sys
 
@@ -83,20 +84,20 @@ def extract(model, dims, like):
     return layers
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--reference", required=True, help="checkout of Coolzyh/Globecom2020-ResourceAllocationGNN")
-    ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
-    ap.add_argument("--batches", type=int, nargs="+", default=[1, 64, 256])
-    a = ap.parse_args()
-    sys.path.insert(0, a.reference)
-    import keras                                  # noqa: F401  (fails loudly if the pinned stack is missing)
+def generate(reference, out, batches, prefix="tf1", require_pinned_stack=True):
+    """Drive the reference's own BS class (imported from `reference`) and write {prefix}_n4_b{B}.npz for every B."""
+    sys.path.insert(0, reference)
+    import keras                                  # noqa: F401  (fails loudly if the stack is missing)
     import tensorflow as tf
-    assert keras.__version__.startswith("2.2") and tf.__version__.startswith("1.14"), (keras.__version__, tf.__version__)
+    if require_pinned_stack:
+        assert keras.__version__.startswith("2.2") and tf.__version__.startswith("1.14") and "shim" not in keras.__version__, \
+            (keras.__version__, tf.__version__)
     from BS_brain import BS                       # the reference's own class, unmodified
     dims = O.BrainDims(N, 3, 1, F, 1, CH, stages=S, per_slot=True)
-    for B in a.batches:
+    for B in batches:
         rng = np.random.default_rng(1001 + B)     # the reference's training seed (RL_Train_main.py:44) + batch
+        np.random.seed(1001 + B)                  # Keras' fit shuffles with the global generator (RL_Train_main.py:45-47)
+        random.seed(1001 + B)
         brain = BS(N, 3, 1, F, 1, CH)
         online = O.init_params(dims, rng, dtype=np.float32, bias_scale=0.05)
         target = O.init_params(dims, rng, dtype=np.float32, bias_scale=0.05)
@@ -120,12 +121,21 @@ def main():
         brain.update_target_model()
         synced = extract(brain.target_model, dims, online)
         assert all(np.array_equal(s["W"], t["W"]) for s, t in zip(synced, after))
-        np.savez_compressed(os.path.join(a.out, f"tf1_n4_b{B}.npz"), N=N, S=S, per_slot=1, F=F, CH=CH,
+        np.savez_compressed(os.path.join(out, f"{prefix}_n4_b{B}.npz"), N=N, S=S, per_slot=1, F=F, CH=CH,
                             node=node, edge=edge, adj=adj.astype(np.float32), params=O.flatten_params(online),
                             target_params=O.flatten_params(target), q=q, q_target=q_t, actions=actions, rewards=rewards,
                             y=y, loss=float(hist.history["loss"][0]), per_head=per_head,
                             params_after_fit=O.flatten_params(after), keras=keras.__version__, tensorflow=tf.__version__)
-        print(f"wrote tf1_n4_b{B}.npz: loss {hist.history['loss'][0]:.6f}")
+        print(f"wrote {prefix}_n4_b{B}.npz: loss {hist.history['loss'][0]:.6f}")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reference", required=True, help="checkout of Coolzyh/Globecom2020-ResourceAllocationGNN")
+    ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
+    ap.add_argument("--batches", type=int, nargs="+", default=[1, 64, 256])
+    a = ap.parse_args()
+    generate(a.reference, a.out, a.batches)
 
 
 if __name__ == "__main__":
