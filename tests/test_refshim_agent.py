@@ -161,4 +161,16 @@ def test_engine_reproduces_the_reference_replay_and_greedy_actions(rec):
     np.testing.assert_allclose(q_max, rec["Q_max_mean"], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(oq_mean, rec["Orig_Q_mean"], rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(oq_max, rec["Orig_Q_max_mean"], rtol=1e-4, atol=1e-5)
-    assert np.abs(agent.brain.get_flat_params(0) - rec["params_after_fit"]).max() <= 2e-6
+    # weights after the step: same three-part statement as tests/test_tf1_golden.py::_check_weights_after_fit
+    d = _dims(rec)
+    f64 = lambda a: np.asarray(a, np.float64)
+    _, _, g_ref = O.brain_backward(d, O.unflatten_params(d, f64(rec["params"])), f64(rec["node"][idx]), f64(rec["edge"][idx]),
+                                   f64(rec["adj"][idx]), f64(rec["y"]), q_for_loss=f64(rec["p"]))
+    g_ref, g_dev = O.flatten_params(g_ref), agent.brain.get_flat_params(2).astype(np.float64)
+    scale = np.abs(g_ref).max()
+    assert np.abs(g_dev - g_ref).max() <= 1e-5 * scale + 4e-6
+    p1 = agent.brain.get_flat_params(0)
+    pa, _, _ = O.keras_adam_step(f64(rec["params"]), g_dev, 0.0, 0.0, 1)
+    assert np.abs(pa - p1).max() <= 1e-6
+    dev, well = np.abs(p1 - rec["params_after_fit"]), np.abs(g_ref) >= 1e-4 * scale
+    assert well.mean() > 0.3 and dev[well].max() <= 2e-6 and dev.max() <= 1.1e-3

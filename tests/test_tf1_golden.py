@@ -72,6 +72,32 @@ def test_committed_shim_vectors_are_what_the_reference_produces_now(tmp_path):
                 assert np.array_equal(a[k], b[k]), (os.path.basename(p), k)
 
 
+def _check_weights_after_fit(brain, z):
+    """Post-fit weights.  The first Adam step is lr * g / (|g| + eps / sqrt(1 - beta2)): a sign-like step of 1e-3 for any
+    |g| >> 3e-6.  DQN targets equal the network's own output except at the taken action (BS_brain.py:683-690), so most
+    residuals are EXACTLY zero for the implementation that produced the targets and ~1e-7 (float32 rounding of q) for
+    any other one; Adam turns that into steps of up to lr on weights whose gradient is below ~1e-5.  Hence three checks:
+    the device gradient equals the oracle's on the recording's residuals up to that floor (1e-5 of the gradient scale +
+    4e-6; measured 2.6e-6 at B = 1, 5e-7 at B = 64), the device Adam step is exact given the device gradient (1e-6), and
+    the weights equal the recording to 2e-6 wherever the recording's gradient is above the floor -- and never differ by
+    more than one step anywhere."""
+    d = O.BrainDims(int(z["N"]), stages=int(z["S"]), per_slot=bool(z["per_slot"]))
+    f64 = lambda k: np.asarray(z[k], np.float64)
+    L = O.unflatten_params(d, f64("params"))
+    g_dev = brain.get_flat_params(2).astype(np.float64)
+    p1 = brain.get_flat_params(0)
+    _, _, g_ref = O.brain_backward(d, L, f64("node"), f64("edge"), f64("adj"), f64("y"), q_for_loss=f64("q"))
+    g_ref = O.flatten_params(g_ref)
+    scale = np.abs(g_ref).max()
+    assert np.abs(g_dev - g_ref).max() <= 1e-5 * scale + 4e-6
+    pa, _, _ = O.keras_adam_step(f64("params"), g_dev, 0.0, 0.0, 1)
+    assert np.abs(pa - p1).max() <= 1e-6
+    dev = np.abs(p1 - z["params_after_fit"])
+    well = np.abs(g_ref) >= 1e-4 * scale
+    assert well.mean() > 0.3 and dev[well].max() <= 2e-6
+    assert dev.max() <= 1.1e-3
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("path", CASES)
 def test_engine_reproduces_reference_model_code(v2v, path):
@@ -92,6 +118,6 @@ def test_engine_reproduces_reference_model_code(v2v, path):
     assert abs(h.history["loss"][0] - float(z["loss"])) <= 1e-4 * abs(float(z["loss"]))
     for k in range(N):
         assert abs(h.history[f"D{k + 1}_Decide_Output_loss"][0] - z["per_head"][k]) <= 1e-4 * z["per_head"].max()
-    assert np.abs(brain.get_flat_params(0) - z["params_after_fit"]).max() <= 2e-6
+    _check_weights_after_fit(brain, z)
     brain.update_target_model()
     assert np.array_equal(brain.get_flat_params(1), brain.get_flat_params(0))
