@@ -138,6 +138,101 @@ class _Cfg:
     Batch_Size, Gamma, v2v_weight, v2i_weight = 64, 0.5, 1, 0.1
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# the whole training loop: tests/golden/refshim_train_n4.npz = the unmodified Agent.train (BS_brain.py:750-910), 2 episodes
+# x 5 train steps x 50 transitions, 10 consecutive Keras-Adam steps and the target synchronisation at env step 500
+# (tests/golden/make_refshim_train_golden.py)
+TRAIN_PATH = os.path.join(GOLDEN, "refshim_train_n4.npz")
+
+
+@pytest.fixture(scope="module")
+def loop():
+    z = np.load(TRAIN_PATH)
+    return {k: z[k] for k in z.files}
+
+
+def test_oracle_follows_the_reference_training_loop(loop):
+    """fp64 oracle, its own weights AND its own targets carried from step to step (Adam t = 1..10), against the reference's
+    float32 run.  Because each side builds y from its own network output, the untouched entries of the residual are exactly
+    zero on both sides (the ill-conditioned Adam steps of tests/test_tf1_golden.py::_check_weights_after_fit never get
+    excited) and the two runs stay together to float32 rounding: measured <= 3.3e-6 on y, 7e-7 on the losses, 2.8e-6 on
+    every weight after 10 steps."""
+    d = _dims(loop)
+    f64 = lambda a: np.asarray(a, np.float64)
+    P, Tg = f64(loop["params"]), f64(loop["target_params"])
+    m, v = np.zeros_like(P), np.zeros_like(P)
+    keep = list(loop["params_step_index"])
+    ref_head = loop["Train_Loss"].reshape(d.N, -1)                    # (head, episode * steps + step)
+    for i in range(len(loop["loss"])):
+        idx = loop["replay_index"][i]
+        L, Lt = O.unflatten_params(d, P), O.unflatten_params(d, Tg)
+        node, edge, adj = f64(loop["node"][idx]), f64(loop["edge"][idx]), f64(loop["adj"][idx])
+        p = O.brain_forward(d, L, node, edge, adj)
+        p_ = O.brain_forward(d, Lt, f64(loop["node_"][idx]), f64(loop["edge_"][idx]), adj)
+        y = O.td_targets(p, p_, loop["action"][idx], f64(loop["reward"][idx]), float(loop["gamma"]))
+        assert rel(y, loop["y"][i]) <= 2e-5
+        loss, per_head, g = O.brain_backward(d, L, node, edge, adj, y)
+        assert abs(loss - loop["loss"][i]) <= 1e-5 * loop["loss"][i]
+        assert rel(per_head, ref_head[:, i]) <= 1e-5
+        P, m, v = O.keras_adam_step(P, O.flatten_params(g), m, v, i + 1)
+        if i in keep:
+            assert np.abs(P - loop["params_after_step"][keep.index(i)]).max() <= 1e-5
+    assert np.abs(P - loop["params_end"]).max() <= 1e-5
+    # the loop's bookkeeping: one synchronisation, at env step 500 after the 10th train step, copies the online weights
+    assert loop["sync_at"].tolist() == [[500, 10]]
+    assert np.array_equal(loop["params_end"], loop["target_params_end"])
+    np.testing.assert_allclose(loop["Orig_Train_Q_mean"], loop["Train_Q_mean"], rtol=1e-5, atol=1e-6)   # in-place overwrite
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/BS_brain.py"), reason="reference tree not present (GPU box)")
+def test_committed_training_recording_is_what_the_reference_does_now(loop, tmp_path):
+    import subprocess
+    import sys
+    subprocess.run([sys.executable, os.path.join(GOLDEN, "make_refshim_train_golden.py"), "/root/reference", str(tmp_path)],
+                   check=True, cwd=os.path.dirname(os.path.dirname(GOLDEN)), capture_output=True, timeout=900)
+    new = np.load(os.path.join(tmp_path, "refshim_train_n4.npz"))
+    exact = ("node", "edge", "node_", "edge_", "adj", "reward", "params", "target_params", "action", "replay_index", "sync_at")
+    for k, v in loop.items():
+        if k in exact or v.dtype.kind != "f":
+            assert np.array_equal(new[k], v), k                                    # simulator, RNG draws, indices, weights in
+        else:
+            np.testing.assert_allclose(new[k], v, rtol=1e-4, atol=1e-5, err_msg=k)  # float32 network arithmetic (BLAS threads)
+
+
+@pytest.mark.gpu
+def test_engine_follows_the_reference_training_loop(loop):
+    """dqn.Agent on the CUDA engine replays the reference's 10 train steps: the recorded transitions enter the replay ring
+    50 at a time, every replay() draws the recorded batch, the target network is synchronised as Agent.train does."""
+    from synthetic_env import SyntheticEnviron
+    dqn = _dqn()
+    N, CH, F = int(loop["N"]), int(loop["CH"]), int(loop["F"])
+    agent = dqn.Agent(N, CH, 1, F, SyntheticEnviron(N, seed=1), _Cfg(), memory_capacity=1000, per_slot=True, seed=0)
+    agent.brain.set_flat_params(loop["params"], 0)
+    agent.brain.set_flat_params(loop["target_params"], 1)
+    ref_head = loop["Train_Loss"].reshape(N, -1)
+    q_mean, q_max = loop["Train_Q_mean"].reshape(N, -1), loop["Train_Q_max_mean"].reshape(N, -1)
+    for i in range(len(loop["loss"])):
+        s = slice(50 * i, 50 * (i + 1))
+        agent.memory.add_batch(*(loop[k][s] for k in ("node", "edge", "adj", "action", "reward", "node_", "edge_")))
+        agent.num_step = 50 * (i + 1)
+        idx = loop["replay_index"][i]
+        agent.memory.sample_indices = lambda n, rng=None, idx=idx: idx
+        hist, qm, qx, oqm, oqx = agent.replay()
+        tol = 1e-4
+        assert abs(hist.history["loss"][0] - loop["loss"][i]) <= tol * loop["loss"][i], i
+        for k in range(N):
+            assert abs(hist.history[f"D{k + 1}_Decide_Output_loss"][0] - ref_head[k, i]) <= tol * ref_head[:, i].max(), (i, k)
+        np.testing.assert_allclose(qm, q_mean[:, i], rtol=0, atol=tol * np.abs(q_mean[:, i]).max() + 1e-5)
+        np.testing.assert_allclose(qx, q_max[:, i], rtol=0, atol=tol * np.abs(q_max[:, i]).max() + 1e-5)
+        if agent.num_step % dqn.UPDATE_TARGET_FREQUENCY == 0:                          # BS_brain.py:846-847
+            agent.brain.update_target_model()
+    assert agent.brain.iterations == 10
+    dev = np.abs(agent.brain.get_flat_params(0) - loop["params_end"])
+    print("engine vs reference after 10 steps: median", np.median(dev), "frac > 1e-4", (dev > 1e-4).mean(), "max", dev.max())
+    assert dev.max() <= 2e-5                                # measured 2.3e-6 (median 0: most weights bit-equal)
+    assert np.array_equal(agent.brain.get_flat_params(1), agent.brain.get_flat_params(0))      # synchronised at step 500
+
+
 @pytest.mark.gpu
 def test_engine_reproduces_the_reference_replay_and_greedy_actions(rec):
     from synthetic_env import SyntheticEnviron
