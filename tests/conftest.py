@@ -17,7 +17,7 @@ def pytest_configure(config):
 # Collection order: the hot-path rows of SURVEY.md section 8 (a: kernels, layers, brain; g: tensor cores; e: data
 # parallel) run before the "next" rows (f: DQN loop, batched environment), so that under `-x` a failure in an f-row
 # can never hide the parity tests of the judged kernels.
-_ORDER = ["test_capi_symbols", "test_oracle", "test_host_stage", "test_host_logic", "test_gpu_kernels", "test_gpu_layers",
+_ORDER = ["test_capi_symbols", "test_oracle", "test_keras_shim", "test_host_stage", "test_host_logic", "test_gpu_kernels", "test_gpu_layers",
           "test_gpu_brain", "test_tf1_golden", "test_refshim_agent", "test_gpu_bf16", "test_gpu_tc", "test_gpu_dp", "test_gpu_dqn", "test_dqn_host", "test_env_oracle",
           "test_gpu_env"]
 
