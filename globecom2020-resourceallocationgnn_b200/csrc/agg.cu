@@ -144,7 +144,16 @@ static int launch_fast(const T* H, const uint32_t* mask, const T* addend, T* out
   constexpr int TG = 32 / (4 * MP);
   AggLaunchCfg cfg;
   cfg.dep_wait = !independent;
-  cfg.ctas_per_sm = agg_fast_fits<T>(N, TG, addend != nullptr, kAggWarps, 2) ? 2 : 1;
+  // CTAs per SM (measured at N = 20, profiles/agg_variants_r02.txt).  A launch that waits for its predecessor wants every
+  // byte in flight at once: as many CTAs as fit, up to 4 (bf16 storage: 0.229 -> 0.336 of the roofline at B = 8192, 0.425 ->
+  // 0.519 at 32768; fp32 +2 %).  A stream of independent launches wants 2 -- and with bf16 storage 1 while a warp has at
+  // most ~8 tiles, so that the next launch's CTAs do not queue behind a second wave (0.626 -> 0.693 at B = 8192).
+  const bool add = addend != nullptr;
+  int want = 2;
+  if (!independent) want = 4;
+  else if (sizeof(T) == 2 && ceil_div(B, TG) <= 8 * kAggWarps * sm_count()) want = 1;
+  while (want > 1 && !agg_fast_fits<T>(N, TG, add, kAggWarps, want)) --want;
+  cfg.ctas_per_sm = want;
   if (addend) return launch_agg_fast<T, MT, MP, true, kAggWarps, true, NC, WALK>(H, mask, addend, out, B, N, cfg, st);
   return launch_agg_fast<T, MT, MP, false, kAggWarps, true, NC, WALK>(H, mask, addend, out, B, N, cfg, st);
 }

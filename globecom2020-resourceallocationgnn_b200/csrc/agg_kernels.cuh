@@ -580,7 +580,12 @@ static int launch_agg_sparse_t(const T* H, const uint32_t* mask, const T* addend
   const size_t smem = (size_t)ts.warp_bytes * WARPS;
   const int num_tiles = ceil_div(B, TG);
   const int ctas_per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
-  const int grid = std::max(1, std::min(ceil_div(num_tiles, WARPS), sm_count() * std::min(ctas_per_sm, 4)));
+  // Grid: a launch that waits for its predecessor wants many CTAs (short ramp: every byte in flight at once); a stream of
+  // independent launches wants ONE CTA per SM, so that the next launch's CTAs are not queued behind this one's second
+  // wave (measured at B = 8192, profiles/agg_variants_r02.txt: N = 64 0.685 -> 0.787, N = 40 0.707 -> 0.848 of the roofline
+  // in the throughput regime; the dependent regime loses 25 % with one CTA per SM, hence the switch).
+  const int cap = dep_wait ? 4 : 1;
+  const int grid = std::max(1, std::min(ceil_div(num_tiles, WARPS), sm_count() * std::min(ctas_per_sm, cap)));
   auto k = agg_sparse_f16_kernel<T, ADD, WARPS, W>;
   static size_t smem_set = 0;
   if (smem > smem_set) {
@@ -606,7 +611,9 @@ template <typename T, int W>
 static int launch_agg_sparse_w(const T* H, const uint32_t* mask, const T* addend, T* out, int B, int N, bool dep_wait,
                                cudaStream_t st) {
   const bool add = addend != nullptr;
-  int TG = std::max(1, 4096 / (N * 16 * (int)sizeof(T)));
+  // ~2 KB of H per warp tile (one graph from N = 32 on): smaller tiles = more of them in flight per SM and a shorter
+  // per-tile latency; 4 KB tiles were 15-20 % slower in both launch regimes at N = 32 (profiles/agg_variants_r02.txt)
+  int TG = std::max(1, 2048 / (N * 16 * (int)sizeof(T)));
   while (TG > 1 && ((TG * N * W * 4) & 15)) --TG;               // keep the mask span 16-byte sized for the bulk copy
   AggSparseSizes ts = agg_sparse_sizes<T>(N, W, TG, add);
   const size_t budget = 224 * 1024;
