@@ -621,7 +621,9 @@ def run_c1(a, v2v, lib, dev):
                         "h2d_bytes_per_step": 256 * N * (9 + 4) * 4 + 256 * N * 4, "d2h_bytes_per_step": 256 * N * CH * 4},
                 "cpu_baseline": {"value": p256["cpu_reference_form_graphs_per_s"], "unit": "graphs/s", "cores": cores, "kind": "port",
                                  "sample": "median of 30 reference-form predicts of 256 graphs (chunks of 32), torch-CPU fp32"},
-                "gpu_launches": int(lib.v2v_launch_count() - launches0)})
+                "transition_loop": "one CUDA-graph replay per environment step (simulator kernels, forward, epsilon-greedy "
+                                   "selection, ring write: 13 launches recorded once); the replay step is launched kernel by kernel",
+                "gpu_launches": int(lib.v2v_launch_count() - launches0 + replayed)})
     print(json.dumps(out), flush=True)
 
 
@@ -644,6 +646,7 @@ def run_c4(a, v2v, lib, dev):
                                   "50 transitions per training step, target sync every 500 environment steps", "config": "c4"},
            "points": {}}
     launches0 = lib.v2v_launch_count()
+    replayed = 0
     for E in (1, 256):
         env = v2v.BatchedEnviron(E, n_veh=N, n_rb=4, seed=SEED)
         agent = v2v.BatchedAgent(env, Cfg, memory_capacity=1 << 16, seed=SEED, stages=3, per_slot=True)
@@ -655,6 +658,7 @@ def run_c4(a, v2v, lib, dev):
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         assert np.isfinite(loss).all() and np.isfinite(rew).all()
+        replayed += agent.replayed_kernel_launches
         out["points"][f"E={E}"] = {"train_steps_per_s": steps / dt, "transitions_per_s": steps * 50 * E / dt,
                                    "ms_per_train_step": 1e3 * dt / steps, "final_loss": float(loss[-1, -1].sum()),
                                    "mean_reward": float(rew.mean())}
@@ -665,7 +669,9 @@ def run_c4(a, v2v, lib, dev):
                         "losses and the mean reward come back"},
                 "reference_loop_cost": "the reference spends 9.7 ms per environment step at N=20 / 0.8 ms at N=4 in its Python "
                                        "simulator alone (SURVEY.md 8f-4), i.e. >= 40 ms per training step before any TF call",
-                "gpu_launches": int(lib.v2v_launch_count() - launches0)})
+                "transition_loop": "one CUDA-graph replay per environment step (simulator kernels, forward, epsilon-greedy "
+                                   "selection, ring write: 13 launches recorded once); the replay step is launched kernel by kernel",
+                "gpu_launches": int(lib.v2v_launch_count() - launches0 + replayed)})
     print(json.dumps(out), flush=True)
 
 

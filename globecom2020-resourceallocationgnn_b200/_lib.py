@@ -60,6 +60,8 @@ SIGNATURES = {
                                        c_void_p, C.c_int, c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_void_p]),
     "v2v_huber_loss_grad": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int,
                                       C.c_float, c_void_p]),
+    "v2v_dqn_select_actions": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, c_void_p]),
+    "v2v_dqn_replay_write": (C.c_int, [c_void_p] * 19 + [C.c_int, C.c_long, C.c_int, C.c_int, C.c_int, c_void_p]),
     "v2v_td_target": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_float, c_void_p, C.c_int, C.c_int,
                                 C.c_int, c_void_p]),
     "v2v_adam_step": (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, C.c_long, C.c_int, C.c_float, C.c_float,

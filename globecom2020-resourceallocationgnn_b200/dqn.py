@@ -68,6 +68,11 @@ class ReplayRing:
         self.action, self.reward = z(self.capacity, N, dt=torch.int32), z(self.capacity)
         self.size = 0          # valid slots
         self.head = 0          # next slot to write (FIFO eviction like samples.pop(0), :255-256)
+        # device mirror of `head`: add_device computes its slot indices from it, so that the same launches can be replayed
+        # from a CUDA graph (BatchedAgent) without any host value baked in
+        self.head_dev = torch.zeros((), dtype=torch.int64, device=self.device)
+        self._done = torch.zeros((), dtype=torch.int32, device=self.device)      # scratch of v2v_dqn_replay_write
+        self._arange = {}
 
     def __len__(self):
         return self.size
@@ -95,11 +100,17 @@ class ReplayRing:
                          (self.in_mask, in_m), (self.out_mask, out_m), (self.action, to(action, torch.int32)),
                          (self.reward, to(reward))):
             dst.index_copy_(0, idx_d, src)
+        self._advance(T)
+        self.head_dev.fill_(self.head)
+
+    def _advance(self, T):
+        """Host-side bookkeeping of T appended transitions (the device cursor is advanced by add_device itself)."""
         self.head = int((self.head + T) % self.capacity)
         self.size = min(self.capacity, self.size + T)
 
-    def add_device(self, node, edge, in_mask, out_mask, action, reward, node_, edge_):
-        """Append T transitions that already live on the device (the batched environment's output): no host copy."""
+    def add_device(self, node, edge, in_mask, out_mask, action, reward, node_, edge_, step_dev=None):
+        """Append T transitions that already live on the device (the batched environment's output): no host copy.
+        ``step_dev`` (fp32 device tensor, optional): element 0 is incremented by the same launch (the agent's step counter)."""
         T = int(reward.shape[0])
         if T == 0:
             return
@@ -111,12 +122,27 @@ class ReplayRing:
             if t.device != ref.device or t.dtype != ref.dtype or t.numel() != T * ref[0].numel():
                 raise ValueError(f"ReplayRing.add_device: {name} must be {ref.dtype} on {ref.device} with {T} x "
                                  f"{tuple(ref.shape[1:])} elements, got {t.dtype} {tuple(t.shape)} on {t.device}")
-        idx = (self.head + torch.arange(T, device=self.device)) % self.capacity
-        for dst, src in ((self.node, node), (self.edge, edge), (self.node_, node_), (self.edge_, edge_), (self.in_mask, in_mask),
-                         (self.out_mask, out_mask), (self.action, action.to(torch.int32)), (self.reward, reward)):
-            dst.index_copy_(0, idx, src.reshape((T,) + tuple(dst.shape[1:])))
-        self.head = int((self.head + T) % self.capacity)
-        self.size = min(self.capacity, self.size + T)
+        action = action.to(torch.int32)
+        if self.device.type == "cuda":
+            # one launch writes all eight tensors at the device-side cursor and advances it (csrc/dqn.cu)
+            srcs = [t.contiguous() for t in (node, edge, node_, edge_, in_mask, out_mask, action, reward)]
+            lib = _lib.load()
+            _lib.check(lib.v2v_dqn_replay_write(
+                ptr(self.node), ptr(self.edge), ptr(self.node_), ptr(self.edge_), ptr(self.in_mask), ptr(self.out_mask),
+                ptr(self.action), ptr(self.reward), ptr(srcs[0]), ptr(srcs[1]), ptr(srcs[2]), ptr(srcs[3]), ptr(srcs[4]),
+                ptr(srcs[5]), ptr(srcs[6]), ptr(srcs[7]), ptr(self.head_dev), ptr(step_dev), ptr(self._done), T, self.capacity,
+                self.N, self.Dn, self.De, _lib.current_stream()))
+        else:
+            if T not in self._arange:
+                self._arange[T] = torch.arange(T, device=self.device)
+            idx = (self.head_dev + self._arange[T]) % self.capacity
+            for dst, src in ((self.node, node), (self.edge, edge), (self.node_, node_), (self.edge_, edge_), (self.in_mask, in_mask),
+                             (self.out_mask, out_mask), (self.action, action), (self.reward, reward)):
+                dst.index_copy_(0, idx, src.reshape((T,) + tuple(dst.shape[1:])))
+            self.head_dev.add_(T).remainder_(self.capacity)
+            if step_dev is not None:
+                step_dev[0] += 1.0
+        self._advance(T)
 
     def sample_indices(self, n, rng=np.random):
         """Memory.sample (:258-270): without replacement when enough samples exist, else with replacement."""
@@ -312,11 +338,12 @@ class BatchedAgent:
     that environment draw a uniform random channel, otherwise each link takes the first maximiser of its Q row.
     """
 
-    def __init__(self, environment, curr_rl_config, num_d2d_feedback=16, memory_capacity=1 << 18, seed=None, **brain_kwargs):
+    def __init__(self, environment, curr_rl_config, num_d2d_feedback=16, memory_capacity=1 << 18, seed=None, use_graph=True,
+                 **brain_kwargs):
         self.env = environment
         self.num_D2D, self.num_CH, self.num_Neighbor = environment.n_Veh, environment.n_RB, 1
         self.E = environment.E
-        self.epsilon, self.num_step = MAX_EPSILON, 0
+        self.num_step = 0
         brain_kwargs.setdefault("max_batch", max(curr_rl_config.Batch_Size, self.E))
         if seed is not None:
             brain_kwargs.setdefault("seed", int(seed))      # the same seed fixes the glorot draw (reproducible runs)
@@ -325,39 +352,142 @@ class BatchedAgent:
         self.v2v_weight, self.v2i_weight = curr_rl_config.v2v_weight, curr_rl_config.v2i_weight
         self.memory = ReplayRing(memory_capacity, self.num_D2D, self.brain.num_One_Node_Input, self.brain.num_One_Edge_Input,
                                  device=environment.dev)
-        self.total_steps = 1
         self.gen = torch.Generator(device=environment.dev)
         if seed is not None:
             self.gen.manual_seed(int(seed))
         self._lib = _lib.load()
+        # The epsilon schedule lives on the device ([step, anneal steps, decrement per step, forced value or -1]): a
+        # transition reads nothing from the host, so the whole transition can be replayed from a CUDA graph.
+        self._sched = torch.zeros(4, dtype=torch.float32, device=environment.dev)
+        self._forced_eps = None
+        self.total_steps = 1
+        self.use_graph = bool(use_graph)
+        self._graph = None               # (CUDAGraph, static reward tensor, library kernels per replay) of one transition
+        self._graph_key = None
+        self.replayed_kernel_launches = 0        # launches of this library's kernels executed by graph replays (the library's
+                                                 # own counter, v2v_launch_count, only sees the launch that was captured)
 
-    def _update_epsilon(self):
-        steps = 0.8 * self.total_steps                                                   # :315-324
+    # ------------------------------------------------------------------ epsilon schedule (:315-324), host view + device copy
+    @property
+    def total_steps(self):
+        return self._total_steps
+
+    @total_steps.setter
+    def total_steps(self, v):
+        self._total_steps = v
+        self._push_schedule()
+
+    @property
+    def num_step(self):
+        return self._num_step
+
+    @num_step.setter
+    def num_step(self, v):
+        self._num_step = int(v)
+        if hasattr(self, "_sched"):
+            self._push_schedule()
+
+    @property
+    def epsilon(self):
+        if self._forced_eps is not None:
+            return self._forced_eps
+        steps = 0.8 * self._total_steps
         per_step = (MAX_EPSILON - MIN_EPSILON) / max(steps, 1)
-        self.epsilon = MAX_EPSILON - per_step * self.num_step if self.num_step < steps else MIN_EPSILON
+        return MAX_EPSILON - per_step * self._num_step if self._num_step < steps else MIN_EPSILON
+
+    @epsilon.setter
+    def epsilon(self, v):                # pins epsilon (tests, greedy evaluation); None returns to the schedule
+        self._forced_eps = None if v is None else float(v)
+        self._push_schedule()
+
+    def _push_schedule(self):
+        """Device copy of the schedule: {step, base, decrement per step, floor}, epsilon = max(floor, base - decrement * step)
+        -- the linear anneal of :315-324 (base - decrement * step reaches the floor exactly when the anneal ends)."""
+        if not hasattr(self, "_sched") or not hasattr(self, "_total_steps"):
+            return
+        steps = 0.8 * self._total_steps
+        per_step = (MAX_EPSILON - MIN_EPSILON) / max(steps, 1)
+        vals = [float(self._num_step), MAX_EPSILON, per_step, MIN_EPSILON]
+        if self._forced_eps is not None:
+            vals = [float(self._num_step), self._forced_eps, 0.0, self._forced_eps]
+        self._sched.copy_(torch.tensor(vals, dtype=torch.float32))
 
     def select_actions(self, node, edge, in_mask):
-        """[E, N] int32 channel per link (epsilon-greedy per environment, first maximiser on ties: :342-344)."""
-        self._update_epsilon()
+        """[E, N] int32 channel per link (epsilon-greedy per environment, first maximiser on ties: :342-344); the epsilon
+        test, the arg-max and the selection are one launch (v2v_dqn_select_actions, csrc/dqn.cu)."""
         E, N, dev = self.E, self.num_D2D, self.env.dev
         q = self.brain.forward_device(node, edge, in_mask=in_mask)
-        greedy = torch.argmax(q, dim=2).to(torch.int32)
-        explore = torch.rand((E, 1), generator=self.gen, device=dev) < self.epsilon
+        u = torch.rand((E,), generator=self.gen, device=dev)
         rnd = torch.randint(0, self.num_CH, (E, N), generator=self.gen, device=dev, dtype=torch.int32)
-        return torch.where(explore, rnd, greedy)
+        actions = torch.empty((E, N), dtype=torch.int32, device=dev)
+        _lib.check(self._lib.v2v_dqn_select_actions(ptr(q), ptr(u), ptr(rnd), ptr(self._sched), ptr(actions), E, N, self.num_CH,
+                                                    _lib.current_stream()))
+        return actions
+
+    def _transition(self):
+        """One environment step of every environment into the replay ring (:409-553); everything it reads -- simulator
+        state, weights, epsilon schedule, ring cursor, generator states -- lives on the device.  Returns the reward [E]."""
+        node, edge, im, om = self.env.pack_state()
+        actions = self.select_actions(node, edge, im)
+        _, _, _, reward = self.env.act(actions, self.v2v_weight, self.v2i_weight)           # :366-376, :513-519
+        node_, edge_, _, _ = self.env.pack_state()                                           # the adjacency of s is re-used (:545, :583)
+        self.memory.add_device(node, edge, im, om, actions, reward, node_, edge_, step_dev=self._sched)   # also: step += 1
+        return reward
+
+    def _capture(self):
+        """One transition as a CUDA graph: ~35 small launches (simulator kernels, the brain's forward, action selection,
+        ring writes) become one graph launch -- the loop is launch-bound, not compute-bound."""
+        key = (self.E, self.num_D2D, self.brain._handle, self.memory.capacity)
+        if self._graph is not None and self._graph_key == key:
+            return self._graph
+        # 1. one eager transition off to the side: lazy initialisation (program upload, kernel attributes) must not happen
+        #    inside a capture.  Everything it touched is put back, so that the graph path and the eager path walk through
+        #    the same states (identical trajectories for identical seeds); the ring slots it wrote are overwritten by the
+        #    first real transition.
+        size, head, n_env = self.memory.size, self.memory.head, self.env.n_step
+        saved = (self._sched.clone(), self.memory.head_dev.clone(), self.gen.get_state(), self.env.gen.get_state(),
+                 [t.clone() for t in self._env_state()])
+        self._transition()
+        torch.cuda.synchronize()
+        self._sched.copy_(saved[0]); self.memory.head_dev.copy_(saved[1])
+        self.gen.set_state(saved[2]); self.env.gen.set_state(saved[3])
+        for dst, src in zip(self._env_state(), saved[4]):
+            dst.copy_(src)
+        torch.cuda.synchronize()
+        # 2. capture (records the launches, runs nothing); both generators are registered so that every replay advances them
+        g = torch.cuda.CUDAGraph()
+        g.register_generator_state(self.gen)
+        g.register_generator_state(self.env.gen)
+        n0 = int(self._lib.v2v_launch_count())
+        with torch.cuda.graph(g):
+            reward = self._transition()
+        per_replay = int(self._lib.v2v_launch_count()) - n0
+        self.memory.size, self.memory.head, self.env.n_step = size, head, n_env     # host counters the traced Python advanced
+        self._graph, self._graph_key = (g, reward, per_replay), key
+        return self._graph
+
+    def _env_state(self):
+        e = self.env
+        return [e.pos, e.dir, e.vel, e.v2v_shadow, e.v2i_shadow, e.V2V_channels_with_fastfading, e.V2I_channels_with_fastfading,
+                e.V2I_channels_abs]
 
     def generate_transitions(self, num_transitions):
-        """num_transitions steps of every environment into the replay ring (:409-553); returns rewards [T, E] (device)."""
-        rewards = []
-        for _ in range(num_transitions):
-            node, edge, im, om = self.env.pack_state()
-            actions = self.select_actions(node, edge, im)
-            _, _, _, reward = self.env.act(actions, self.v2v_weight, self.v2i_weight)       # :366-376, :513-519
-            self.num_step += 1
-            node_, edge_, _, _ = self.env.pack_state()                                       # the adjacency of s is re-used (:545, :583)
-            self.memory.add_device(node, edge, im, om, actions, reward, node_, edge_)
-            rewards.append(reward)
-        return torch.stack(rewards)
+        """num_transitions steps of every environment into the replay ring (:409-553); returns rewards [T, E] (device).
+        With ``use_graph`` every step is one replay of the captured transition."""
+        T = int(num_transitions)
+        rewards = torch.empty((T, self.E), dtype=torch.float32, device=self.env.dev)
+        graph = self._capture() if self.use_graph and T > 0 else None
+        for t in range(T):
+            if graph is not None:
+                graph[0].replay()
+                self.replayed_kernel_launches += graph[2]
+                rewards[t].copy_(graph[1])
+                self.memory._advance(self.E)
+                self.env.n_step += 1
+            else:
+                rewards[t].copy_(self._transition())
+            self._num_step += 1
+        return rewards
 
     def replay(self, indices=None):
         """One replay step (:555-748), identical to ``Agent.replay`` but with device-side index sampling.

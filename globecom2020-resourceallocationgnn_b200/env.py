@@ -48,6 +48,7 @@ class BatchedEnviron:
         self.V2I_channels_with_fastfading = torch.zeros((E, N, RB), **f)
         self.V2I_channels_abs = torch.zeros((E, N), **f)
         self.n_step = 0
+        self._shadow_scale = None
 
     # ---------------------------------------------------------------- random draws (plumbing)
     def _randn(self, *shape):
@@ -92,10 +93,19 @@ class BatchedEnviron:
     def renew_channels_fastfading(self, z_v2v=None, z_v2i=None, ff_v2v=None, ff_v2i=None):
         """Environment.py:378-404 (path loss, shadowing AR(1), fast fading) for all environments in one launch."""
         E, N, RB = self.E, self.n_Veh, self.n_RB
-        z_v2v = 3.0 * self._randn(E, N, N) if z_v2v is None else z_v2v          # shadow_std of the V2V links (:55)
-        z_v2i = 8.0 * self._randn(E, N) if z_v2i is None else z_v2i             # :132
-        ff_v2v = self._randn(E, N, N, RB, 2) if ff_v2v is None else ff_v2v
-        ff_v2i = self._randn(E, N, RB, 2) if ff_v2i is None else ff_v2i
+        if z_v2v is None and z_v2i is None and ff_v2v is None and ff_v2i is None:
+            # all four draws from ONE standard-normal launch, the shadowing scales (3 dB V2V :55, 8 dB V2I :132) by one multiply
+            n1, n2, n3, n4 = E * N * N, E * N, E * N * N * RB * 2, E * N * RB * 2
+            z = self._randn(n1 + n2 + n3 + n4)
+            if self._shadow_scale is None:
+                self._shadow_scale = torch.cat([torch.full((n1,), 3.0, device=self.dev), torch.full((n2,), 8.0, device=self.dev)])
+            z[:n1 + n2].mul_(self._shadow_scale)
+            z_v2v, z_v2i, ff_v2v, ff_v2i = z[:n1], z[n1:n1 + n2], z[n1 + n2:n1 + n2 + n3], z[n1 + n2 + n3:]
+        else:
+            z_v2v = 3.0 * self._randn(E, N, N) if z_v2v is None else z_v2v          # shadow_std of the V2V links (:55)
+            z_v2i = 8.0 * self._randn(E, N) if z_v2i is None else z_v2i             # :132
+            ff_v2v = self._randn(E, N, N, RB, 2) if ff_v2v is None else ff_v2v
+            ff_v2i = self._randn(E, N, RB, 2) if ff_v2i is None else ff_v2i
         _lib.check(self._lib.v2v_env_renew_channels(
             ptr(self.pos), ptr(self.vel), ptr(self.v2v_shadow), ptr(self.v2i_shadow), ptr(z_v2v), ptr(z_v2i), ptr(ff_v2v), ptr(ff_v2i),
             ptr(self.V2V_channels_with_fastfading), ptr(self.V2I_channels_with_fastfading), ptr(self.V2I_channels_abs), E, N, RB,

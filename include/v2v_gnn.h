@@ -128,6 +128,25 @@ int v2v_td_target(const float* p_dev, const float* p_next_dev, const int32_t* ac
                   const float* reward_dev, float gamma, float* y_dev,
                   int B, int N, int CH, void* stream);
 
+/* Epsilon-greedy action selection of Agent.select_action_while_training (BS_brain.py:308-352) for E environments:
+ * sched_dev fp32 [4] = {environment step, base, decrement per step, floor}; epsilon = max(floor, base - decrement * step)
+ * (the linear anneal of :315-324).  Environment e explores when u_explore_dev[e] < epsilon: every link takes its entry of
+ * random_action_dev [E][N] (:330-333); otherwise link (e, n) takes the FIRST maximiser of q_dev[e][n][:] (:336-344). */
+int v2v_dqn_select_actions(const float* q_dev, const float* u_explore_dev, const int32_t* random_action_dev,
+                           const float* sched_dev, int32_t* action_dev, int E, int N, int CH, void* stream);
+
+/* Memory.add (BS_brain.py:252-256) for a device-resident ring of `capacity` slots: transition t of T goes to slot
+ * (*head_dev + t) % capacity of every ring tensor (node / node_next [.][N][Dn], edge / edge_next [.][N][De], the two
+ * adjacency mask orientations [.][N][ceil(N/32)], action [.][N], reward [.]); then *head_dev advances by T (mod capacity)
+ * and, if step_dev is not NULL, *step_dev += 1 -- all on the device, so the launch can be replayed from a CUDA graph.
+ * done_dev: one zero-initialised unsigned int of scratch. */
+int v2v_dqn_replay_write(float* ring_node, float* ring_edge, float* ring_node_next, float* ring_edge_next,
+                         int32_t* ring_in_mask, int32_t* ring_out_mask, int32_t* ring_action, float* ring_reward,
+                         const float* node, const float* edge, const float* node_next, const float* edge_next,
+                         const int32_t* in_mask, const int32_t* out_mask, const int32_t* action, const float* reward,
+                         long long* head_dev, float* step_dev, unsigned* done_dev, int T, long capacity, int N, int Dn,
+                         int De, void* stream);
+
 /* keras.optimizers.Adam(lr, beta_1, beta_2) update rule of Keras 2.2.4
  * (BS_brain.py:212), epsilon outside the sqrt; t = 1-based iteration,
  * grad_scale multiplies g first (1/world_size after a sum all-reduce). */

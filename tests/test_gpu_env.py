@@ -165,3 +165,36 @@ def test_batched_dqn_loop_on_device(v2v):
     a = agent.select_actions(node, edge, im)
     q = agent.brain.forward_device(node, edge, in_mask=im)
     assert torch.equal(a, torch.argmax(q, dim=2).to(torch.int32)) and int(a.min()) >= 0 and int(a.max()) < 4
+
+
+def test_graph_replayed_transitions_equal_eager_transitions(v2v):
+    """BatchedAgent.generate_transitions replays ONE captured CUDA graph per environment step; with the same seeds it must
+    walk through exactly the states the launch-by-launch path walks through (simulator, replay ring, epsilon, rewards)."""
+    class Cfg:
+        Batch_Size, Gamma, v2v_weight, v2i_weight = 64, 0.5, 1.0, 0.1
+    E, N = 16, 4
+    runs = []
+    for use_graph in (False, True):
+        env = v2v.BatchedEnviron(E, n_veh=N, n_rb=4, seed=11)
+        agent = v2v.BatchedAgent(env, Cfg, memory_capacity=256, seed=13, stages=3, per_slot=True, use_graph=use_graph)
+        agent.total_steps, agent.num_step = 40, 0
+        env.new_random_game()
+        r1 = agent.generate_transitions(9)
+        losses, _, _ = agent.replay(indices=torch.arange(64, device=env.dev))
+        r2 = agent.generate_transitions(12)                          # wraps around the 256-slot ring (21 * 16 = 336 > 256)
+        torch.cuda.synchronize()
+        assert (agent._graph is not None) == use_graph
+        m = agent.memory
+        runs.append(dict(r1=r1, r2=r2, losses=losses, eps=agent.epsilon, step=agent.num_step, size=m.size, head=m.head,
+                         head_dev=int(m.head_dev.item()), sched=agent._sched.clone(), n_env=env.n_step,
+                         ring=[t.clone() for t in (m.node, m.edge, m.node_, m.edge_, m.in_mask, m.out_mask, m.action, m.reward)],
+                         env=[t.clone() for t in agent._env_state()]))
+    a, b = runs
+    assert a["step"] == b["step"] == 21 and a["size"] == b["size"] == 256 and a["head"] == b["head"] == b["head_dev"] == (21 * E) % 256
+    assert a["n_env"] == b["n_env"] and a["eps"] == b["eps"] and 0.01 < a["eps"] < 1.0
+    assert torch.equal(a["sched"], b["sched"]) and float(a["sched"][0]) == 21.0
+    for k in ("r1", "r2", "losses"):
+        assert torch.equal(a[k], b[k]), k
+    for x, y in zip(a["ring"] + a["env"], b["ring"] + b["env"]):
+        assert torch.equal(x, y)
+    assert a["r1"].shape == (9, E) and torch.isfinite(a["r2"]).all() and float(a["r1"].min()) >= 0.0
