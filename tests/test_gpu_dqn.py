@@ -74,3 +74,51 @@ def test_short_training_run_on_synthetic_environment(tmp_path):
     assert not np.array_equal(agent.brain.get_flat_params(0), agent.brain.get_flat_params(1))
     rewards = agent.test_run(2, 5)
     assert rewards.shape == (2, 5) and np.isfinite(rewards).all()
+
+
+def test_select_actions_kernel_follows_the_reference_rule(v2v):
+    """v2v_dqn_select_actions against Agent.select_action_while_training (BS_brain.py:308-352) restated in NumPy: linear
+    epsilon anneal (:315-324), one explore decision per environment (:330-333), FIRST maximiser on ties (:342-344)."""
+    lib, L = v2v.load_library(), v2v._lib
+    rng = np.random.default_rng(0)
+    E, N, CH = 300, 5, 4
+    q = rng.normal(size=(E, N, CH)).astype(np.float32)
+    q[::7, :, 2] = q[::7, :, 0] = q[::7].max(axis=2) + 1.0           # ties: columns 0 and 2 share the maximum -> 0 wins
+    u = rng.random(E).astype(np.float32)
+    rnd = rng.integers(0, CH, (E, N)).astype(np.int32)
+    for step, total in ((0, 1000), (400, 1000), (799, 1000), (800, 1000), (5000, 1000)):
+        steps = 0.8 * total
+        per_step = (1 - 0.01) / steps
+        eps = 1 - per_step * step if step < steps else 0.01                              # the reference's branch form
+        sched = torch.tensor([step, 1.0, per_step, 0.01], dtype=torch.float32, device="cuda")
+        out = torch.empty((E, N), dtype=torch.int32, device="cuda")
+        qd, ud, rd = (torch.from_numpy(a).cuda() for a in (q, u, rnd))
+        L.check(lib.v2v_dqn_select_actions(qd.data_ptr(), ud.data_ptr(), rd.data_ptr(), sched.data_ptr(), out.data_ptr(), E, N, CH,
+                                           L.current_stream()))
+        explore = u < np.float32(eps)
+        want = np.where(explore[:, None], rnd, q.argmax(axis=2).astype(np.int32))         # np.argmax: first maximiser
+        near = np.abs(u - eps) < 1e-6                                                      # float32 rounding of the schedule
+        assert np.array_equal(out.cpu().numpy()[~near], want[~near]), step
+        assert (want[::7][~explore[::7]] == 0).all()
+
+
+def test_replay_write_kernel_is_memory_add(v2v):
+    """v2v_dqn_replay_write against Memory.add (BS_brain.py:252-256) as the CPU ring implements it: FIFO slots modulo the
+    capacity, wrap-around inside one call, device cursor and step counter advanced by the same launch."""
+    dqn = _dqn()
+    N, cap, Dn, De = 5, 23, 9, 4
+    gpu, cpu = dqn.ReplayRing(cap, N, Dn, De, device="cuda"), dqn.ReplayRing(cap, N, Dn, De, device="cpu")
+    step = torch.zeros(4, device="cuda")
+    g = torch.Generator().manual_seed(0)
+    for T in (7, 7, 7, 7, 23, 1):                                  # 4th call wraps (21 + 7 > 23); 5th rewrites every slot
+        t = dict(node=torch.randn(T, N, Dn, generator=g), edge=torch.randn(T, N, De, generator=g),
+                 in_mask=torch.randint(0, 32, (T, N, 1), generator=g, dtype=torch.int32),
+                 out_mask=torch.randint(0, 32, (T, N, 1), generator=g, dtype=torch.int32),
+                 action=torch.randint(0, 4, (T, N), generator=g, dtype=torch.int32), reward=torch.randn(T, generator=g),
+                 node_=torch.randn(T, N, Dn, generator=g), edge_=torch.randn(T, N, De, generator=g))
+        cpu.add_device(**t)
+        gpu.add_device(**{k: v.cuda() for k, v in t.items()}, step_dev=step)
+        assert gpu.head == cpu.head == int(gpu.head_dev.item()) and gpu.size == cpu.size
+        for name in ("node", "edge", "node_", "edge_", "in_mask", "out_mask", "action", "reward"):
+            assert torch.equal(getattr(gpu, name).cpu(), getattr(cpu, name)), (T, name)
+    assert float(step[0]) == 6.0 and float(step[1:].abs().sum()) == 0.0 and int(gpu._done.item()) == 0
