@@ -51,6 +51,31 @@ static inline void transpose32(uint32_t a[32]) {
   }
 }
 
+// Copy into pinned staging with non-temporal stores: the destination is read next by the copy engine, not by a core, so
+// there is no point in pulling its cache lines in (write-allocate) or in keeping them.  dst 16-byte aligned, n floats.
+static inline void stream_copy_f32(float* dst, const float* src, size_t n) {
+#if defined(__SSE2__)
+  static const bool on = [] { const char* e = getenv("V2V_HOST_NT"); return !(e && e[0] == '0'); }();
+  if (on && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && n >= 1024) {
+    size_t i = 0;
+    for (; i + 16 <= n; i += 16) {
+      const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
+      const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 4));
+      const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 8));
+      const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 12));
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), a);
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 4), b);
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 8), c);
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 12), d);
+    }
+    for (; i < n; ++i) dst[i] = src[i];
+    _mm_sfence();
+    return;
+  }
+#endif
+  memcpy(dst, src, n * sizeof(float));
+}
+
 namespace {
 
 struct Job {                                        // one host_stage_run call; kept alive by whoever still looks at it
@@ -138,7 +163,8 @@ class StagePool {
     const S* src = static_cast<const S*>(v.ptr);
     const bool plain_f32 = std::is_same<S, float>::value && v.col_stride == 1 && c.check == 0;
     if (plain_f32 && v.row_stride == v.cols && v.dst_row_stride == v.cols) {
-      memcpy(c.dst + v.dst_off + c.r0 * v.cols, src + c.r0 * v.cols, (size_t)(c.r1 - c.r0) * v.cols * sizeof(float));
+      stream_copy_f32(c.dst + v.dst_off + c.r0 * v.cols, reinterpret_cast<const float*>(src) + c.r0 * v.cols,
+                      (size_t)(c.r1 - c.r0) * v.cols);
       return 0;
     }
     int nonbinary = 0, nonzero = 0;
