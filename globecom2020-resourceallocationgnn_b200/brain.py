@@ -552,7 +552,7 @@ class BS:
                 hl = np.empty(N, np.float32)
                 hist = History()
                 keys = self._loss_keys
-                hist.history = {"loss": [], **{k: [] for k in keys}}
+                history = {"loss": [], **{k: [] for k in keys}} if int(epochs) != 1 else None
                 for ep in range(int(epochs)):
                     if self._comm is not None:       # data parallel: this rank's rows, fused NVLink exchange + Adam
                         rc = self._lib.v2v_brain_train_views_dp(self._handle, self._comm, na, nn, ea, en, ga, gn, aa, an,
@@ -561,11 +561,16 @@ class BS:
                         rc = self._lib.v2v_brain_train_views(self._handle, na, nn, ea, en, ga, gn, aa, an, ya, yn, B,
                                                              hl.ctypes.data, _lib.current_stream())
                     _lib.check(rc, ValueError)
-                    per_head = hl.astype(np.float64).tolist()
+                    per_head = hl.tolist()                         # float32 values as Python floats (exact)
                     hist.epoch.append(ep)
-                    hist.history["loss"].append(float(sum(per_head)))
-                    for k in range(N):
-                        hist.history[keys[k]].append(per_head[k])
+                    if history is None:                             # the reference's only case: epochs = 1 (:220-221)
+                        history = {"loss": [float(sum(per_head))]}
+                        history.update(zip(keys, ([v] for v in per_head)))
+                    else:
+                        history["loss"].append(float(sum(per_head)))
+                        for k in range(N):
+                            history[keys[k]].append(per_head[k])
+                hist.history = history if history is not None else {"loss": [], **{k: [] for k in keys}}
                 return hist
         B, node, edge, neigh, adj = self._pack_inputs(x)
         ylab = self._pack_labels(y, B)
