@@ -901,10 +901,16 @@ static int train_views_impl(v2v_brain* b, struct v2v_comm* comm, const v2v_host_
   const float* ng = has_neigh ? b->st_neigh : nullptr;
   const uint32_t* im = weighted ? nullptr : b->st_in_mask;
   const uint32_t* om = weighted ? nullptr : b->st_out_mask;
-  if (int rc = comm ? v2v_brain_train_step_dp(b, comm, b->st_node, b->st_edge, ng, im, om, b->st_adj, b->st_y, B, b->head_loss, stream)
-                    : v2v_brain_train_step(b, b->st_node, b->st_edge, ng, im, om, b->st_adj, b->st_y, B, b->head_loss, stream))
+  // The per-head losses are N floats written once by the reduction kernel: on the fused paths it stores them straight into
+  // the pinned (device-addressable) host block, which saves the device-to-host copy and its latency at the end of the
+  // call.  The layered path accumulates them with atomics and keeps the device buffer + copy.
+  const bool direct = b->bf16 || use_fused(b, im, ng);
+  float* hl_out = direct ? b->pin + b->pin_hl : b->head_loss;
+  if (int rc = comm ? v2v_brain_train_step_dp(b, comm, b->st_node, b->st_edge, ng, im, om, b->st_adj, b->st_y, B, hl_out, stream)
+                    : v2v_brain_train_step(b, b->st_node, b->st_edge, ng, im, om, b->st_adj, b->st_y, B, hl_out, stream))
     return rc;
-  V2V_CHECK_CUDA(cudaMemcpyAsync(b->pin + b->pin_hl, b->head_loss, b->N * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (!direct)
+    V2V_CHECK_CUDA(cudaMemcpyAsync(b->pin + b->pin_hl, b->head_loss, b->N * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (comm) if (int rc = v2v_comm_poll_error(comm, stream)) return rc;
   const double t2 = trace ? now() : 0;
   V2V_CHECK_CUDA(cudaStreamSynchronize(st));
