@@ -621,9 +621,7 @@ def run_c1(a, v2v, lib, dev):
                         "h2d_bytes_per_step": 256 * N * (9 + 4) * 4 + 256 * N * 4, "d2h_bytes_per_step": 256 * N * CH * 4},
                 "cpu_baseline": {"value": p256["cpu_reference_form_graphs_per_s"], "unit": "graphs/s", "cores": cores, "kind": "port",
                                  "sample": "median of 30 reference-form predicts of 256 graphs (chunks of 32), torch-CPU fp32"},
-                "transition_loop": "one CUDA-graph replay per environment step (simulator kernels, forward, epsilon-greedy "
-                                   "selection, ring write: 13 launches recorded once); the replay step is launched kernel by kernel",
-                "gpu_launches": int(lib.v2v_launch_count() - launches0 + replayed)})
+                "gpu_launches": int(lib.v2v_launch_count() - launches0)})
     print(json.dumps(out), flush=True)
 
 

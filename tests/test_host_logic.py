@@ -143,3 +143,30 @@ def test_bench_config_is_identical_in_both_arms(monkeypatch):
     assert (a.config, a.stages, a.dtype, a.batch, a.scaling) == ("c2", 2, "f32", 1024, "weak")
     c1 = bench.config_dict(a, 1)
     assert c1 == bench.config_dict(a, 1) and "configs[1]" in c1["workload"] and c1["edges_per_graph"] == 360
+
+
+def test_no_undefined_names_in_entry_points_and_package():
+    """A NameError inside a rarely taken branch of bench.py only shows on the GPU box (it did once: a config's JSON
+    assembly referred to a variable of another config).  Static check: every name a function reads as a global must be
+    defined at module level or be a builtin."""
+    import builtins
+    import glob
+    import symtable
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [os.path.join(ROOT, f) for f in ("bench.py", "__graft_entry__.py", "v2v_gnn_b200.py")]
+    files += glob.glob(os.path.join(ROOT, "globecom2020-resourceallocationgnn_b200", "*.py")) + glob.glob(os.path.join(ROOT, "scripts", "*.py"))
+    bad = []
+    for path in files:
+        src = open(path).read()
+        top = symtable.symtable(src, path, "exec")
+        known = set(top.get_identifiers()) | set(dir(builtins)) | {"__file__", "__name__", "__doc__"}
+
+        def walk(t):
+            for c in t.get_children():
+                if c.get_type() == "function":
+                    for s in c.get_symbols():
+                        if s.is_global() and s.is_referenced() and s.get_name() not in known:
+                            bad.append((os.path.basename(path), c.get_name(), s.get_name()))
+                walk(c)
+        walk(top)
+    assert not bad, bad
