@@ -1,7 +1,7 @@
 """Where do the engine's post-fit weights leave the refshim recording, and how large is the gradient there?"""
 import sys, os
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import importlib
 v2v = importlib.import_module("globecom2020-resourceallocationgnn_b200")
 from oracle import v2v_oracle as O
