@@ -45,6 +45,22 @@ struct RowVec<2> {
   __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
 };
 
+// Packed fp32 FMA (fma.rn.f32x2, sm_100): two IEEE fused multiply-adds per instruction -- bit-identical to two fmaf, half the
+// FMA issue slots.  The register pairs of a 128-bit shared-memory load are free operands; a broadcast operand is duplicated.
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void fma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ float2 unpk2(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+
 template <int TR, int TC, bool SLOT>
 __device__ __forceinline__ void gemm_phase(const FusedOp& op, float* arena, const float* Ws, const int* tab, int RP,
                                            int TGp, int tid) {
@@ -342,7 +358,62 @@ __device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* 
   }
   if (!SLOT) bias_grad(op, op_idx, arena, tab, RP, my_bias, bacc);
   // ---- data gradient of the requested input columns (4 rows x 4 columns per item)
-  if (op.n_dx > 0) {
+  // Item shape of the data gradient.  On the register-owned weight-gradient path (nwt == 0) the block owners are busy with
+  // one long block each, so the data gradient should be finished by the other threads in ONE round: 8 input columns x 4
+  // rows per item when that many items fit the non-owners (half the items, 12 shared-memory vectors per 128 FMAs instead
+  // of 8 per 64, packed FMAs on row pairs).  Every output is the same sum in the same order as in the 4-column form:
+  // bit-identical results.  Traced on the configs[1] tile: `bwd mlp1` 19.2k -> 15.5k cycles; where every thread owns
+  // weight-gradient work (the row-split small layers) the smaller 4-column items balance better and stay.
+  const bool wide = !SLOT && op.nwt == 0 && op.n_dx > 0 && (op.n_dx & 7) == 0 &&
+                    (RP / 4) * (op.n_dx / 8) <= kFusedThreads - min(op.nblk, kFusedThreads);
+  if (wide) {
+    const int row_groups = RP / 4;
+    const int items = row_groups * (op.n_dx / 8);
+    const int4* dz_rows4 = reinterpret_cast<const int4*>(tab + op.dz_tab);
+    for (;;) {
+      const int item = atomicAdd(dx_ctr, 1);
+      if (item >= items) break;
+      const int kg = item / row_groups, rg = item - kg * row_groups;
+      const int r0 = rg * 4;
+      const float* wr[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) wr[i] = Ws + op.w_off + tab[op.dxk_tab + kg * 8 + i] * op.O;
+      unsigned long long acc[8][2];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = pk2(0.f, 0.f);
+      const float* ab = arena + r0;
+#pragma unroll 2
+      for (int o = 0; o < op.O; o += 4) {
+        const int4 zr = dz_rows4[o >> 2];
+        const float4 d0 = *reinterpret_cast<const float4*>(ab + zr.x * RP), d1 = *reinterpret_cast<const float4*>(ab + zr.y * RP);
+        const float4 d2 = *reinterpret_cast<const float4*>(ab + zr.z * RP), d3 = *reinterpret_cast<const float4*>(ab + zr.w * RP);
+        const unsigned long long z[4][2] = {{pk2(d0.x, d0.y), pk2(d0.z, d0.w)}, {pk2(d1.x, d1.y), pk2(d1.z, d1.w)},
+                                            {pk2(d2.x, d2.y), pk2(d2.z, d2.w)}, {pk2(d3.x, d3.y), pk2(d3.z, d3.w)}};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 w = *reinterpret_cast<const float4*>(wr[i] + o);
+          const float ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int oo = 0; oo < 4; ++oo) {
+            const unsigned long long w2 = pk2(ws[oo], ws[oo]);
+            fma2(acc[i][0], z[oo][0], w2);
+            fma2(acc[i][1], z[oo][1], w2);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 lo = unpk2(acc[i][0]), hi = unpk2(acc[i][1]);
+        float4 v = make_float4(lo.x, lo.y, hi.x, hi.y);
+        if (op.gate_tab >= 0) {
+          const float4 g = *reinterpret_cast<const float4*>(arena + tab[op.gate_tab + kg * 8 + i] * RP + r0);
+          v.x = g.x > 0.f ? v.x : 0.f; v.y = g.y > 0.f ? v.y : 0.f;
+          v.z = g.z > 0.f ? v.z : 0.f; v.w = g.w > 0.f ? v.w : 0.f;
+        }
+        *reinterpret_cast<float4*>(arena + tab[op.dx_tab + kg * 8 + i] * RP + r0) = v;
+      }
+    }
+  } else if (op.n_dx > 0) {
     const int row_groups = RP / 4;
     const int items = row_groups * (op.n_dx / 4);
     // Work queue: the threads without weight-gradient work start on the items at once, the block owners join as they
