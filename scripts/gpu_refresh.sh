@@ -1,3 +1,5 @@
+#!/bin/bash
+# One single-GPU gpurun call after a kernel change: GPU suite, smoke, both bench arms, ncu launch list + full capture of the fused kernel.
 TAG=r02n; O=gpurun_out
 timeout 600 python -m pytest tests -m gpu -q > $O/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"; tail -2 $O/pytest_gpu_$TAG.log
 timeout 300 python __graft_entry__.py --smoke > $O/smoke_$TAG.log 2>&1; echo "smoke rc=$?"
