@@ -459,10 +459,18 @@ class BatchedAgent:
         g.register_generator_state(self.gen)
         g.register_generator_state(self.env.gen)
         n0 = int(self._lib.v2v_launch_count())
-        with torch.cuda.graph(g):
-            reward = self._transition()
+        try:
+            with torch.cuda.graph(g):
+                reward = self._transition()
+        except Exception as exc:               # a stack that cannot capture this sequence: keep working, launch by launch
+            import warnings
+            warnings.warn(f"BatchedAgent: CUDA-graph capture of the transition failed ({exc!r}); falling back to "
+                          "launch-by-launch transitions")
+            self.use_graph = False
+            return None
+        finally:
+            self.memory.size, self.memory.head, self.env.n_step = size, head, n_env     # host counters the traced Python advanced
         per_replay = int(self._lib.v2v_launch_count()) - n0
-        self.memory.size, self.memory.head, self.env.n_step = size, head, n_env     # host counters the traced Python advanced
         self._graph, self._graph_key = (g, reward, per_replay), key
         return self._graph
 
