@@ -1,7 +1,7 @@
 #!/bin/bash
 # One multi-GPU gpurun call: the default bench line (BASELINE configs[1], weak scaling, with e2e) at 1, 2, 4, 8 GPUs.
 # usage: gpurun --gpus 8 -- 'bash scripts/gpu_scale_c2.sh'   (scripts/gpu_scale.sh adds the configs[2] weak / strong lines)
-TAG=r02m; O=gpurun_out; mkdir -p $O
+TAG=${1:-r02m}; O=gpurun_out; mkdir -p $O
 for n in 1 2 4 8; do
   if [ "$n" -eq 1 ]; then
     timeout 300 python bench.py --gpus 1 --steps 300 --warmup 20 --no-cpu-baseline > $O/scale_c2_n${n}_$TAG.json 2> $O/scale_c2_n${n}_$TAG.err
