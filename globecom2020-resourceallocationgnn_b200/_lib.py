@@ -75,6 +75,8 @@ SIGNATURES = {
     "v2v_brain_set_fused": (C.c_int, [c_void_p, C.c_int]),
     "v2v_brain_fused_info": (C.c_int, [c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "v2v_fused_set_trace": (C.c_int, [c_void_p]),
+    "v2v_fused_set_mma": (C.c_int, [C.c_int]),
+    "v2v_fused_get_mma": (C.c_int, []),
     "v2v_fused_plan": (C.c_int, [C.POINTER(BrainConfig), C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "v2v_brain_update_target": (C.c_int, [c_void_p, c_void_p]),
     "v2v_brain_get_iterations": (C.c_int, [c_void_p]),

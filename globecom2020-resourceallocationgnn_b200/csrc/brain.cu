@@ -339,6 +339,8 @@ extern "C" int v2v_brain_set_params(v2v_brain* b, int which, const float* host_i
 }
 
 extern "C" int v2v_fused_set_trace(long long* dev_buf) { return fused_set_trace(dev_buf); }
+extern "C" int v2v_fused_set_mma(int mode) { return fused_set_mma(mode); }
+extern "C" int v2v_fused_get_mma(void) { return fused_get_mma(); }
 extern "C" int v2v_tt_set_trace(long long* dev_buf) { return tt_set_trace(dev_buf); }
 
 extern "C" int v2v_brain_set_fused(v2v_brain* b, int enable) {

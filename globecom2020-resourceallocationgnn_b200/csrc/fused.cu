@@ -15,9 +15,14 @@
 // HBM traffic per graph (N=20): 1,040 B features + 80 B mask + 320 B targets in; nothing out but the
 // 35 KB gradient partial per CTA.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "fused.cuh"
+
+#ifndef V2V_TF32_SPLIT_RN
+#define V2V_TF32_SPLIT_RN 0
+#endif
 
 namespace v2v {
 
@@ -478,9 +483,224 @@ __device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* 
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Tensor-core form of the backward contractions of the shared-weight kernel (template parameter MMA of fused_brain_kernel).
+//
+// The tile's operands sit in the feature-major arena (row index fastest) and the weights in shared memory as W[k][o];
+// tcgen05 cannot read the weight gradient's operands in that form for fp32-grade products (no-swizzle MN-major TF32
+// operands read as zeros, scratch/tc_probe_mn.cu) and hi/lo copies of a whole tile do not fit shared memory, so these
+// phases use the register-operand tensor-core instruction instead: mma.sync m16n8k8 TF32 (SASS HMMA.1688.F32.TF32; measured
+// on B200, scratch/hmma_probe.cu: 23 cycles dependent, one per 2.17 cycles per SM) with every product done in three passes
+// (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi; hi = TF32 round-to-nearest, lo = the rounded remainder: the dropped lo*lo term and the
+// two roundings are each <= 2^-24 of |a||b|, i.e. fp32-grade products; fp32 accumulation).  A fragment element is ONE
+// scalar shared-memory load whatever the orientation of the operand, so both gradients of a layer are the same routine:
+//   data grad   dx[kq][r] = gate * sum_o W[kq][o] dz[o][r]      M = kq, N = r (tile rows),   reduction over o
+//   weight grad dW[k][o]  = sum_r in[k][r] dz[o][r]             M = k,  N = o,               reduction over r
+// A warp task is MT x NT blocks of 16 x 8 outputs: every loaded value is split once and used by MT (or NT) blocks, which
+// is what keeps the split arithmetic (5 integer/float instructions per value) below the tensor pipe's time.  Every output
+// element has one owner and a fixed summation order (deterministic).  Columns r >= RP of the last column block read the
+// next arena row (finite values, never stored).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+#if V2V_TF32_SPLIT_RN
+  // round-to-nearest (ties away) on the bit pattern: finite inputs only, which the arena guarantees
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  const float r = x - __uint_as_float(hi);
+  lo = (__float_as_uint(r) + 0x1000u) & 0xffffe000u;
+#else
+  // truncating split, two instructions per value: hi = the upper 19 bits, lo = the exact remainder (13 bits), handed to
+  // the tensor core as it is (the TF32 datapath reads the upper 19 bits of a 32-bit operand)
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+#endif
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ int warp_next(int* ctr, int lane) {
+  int v = 0;
+  if (lane == 0) v = atomicAdd(ctr, 1);
+  return __shfl_sync(0xffffffffu, v, 0);
+}
+
+// One reduction step of a 16 x (8 NT) task: a = the 4 A-fragment values, b[j] = the 2 B-fragment values of column block j.
+// The three passes run pass-major over the NT blocks (volatile keeps that order): consecutive tensor-core instructions are
+// independent, the next pass on the same accumulator is NT instructions away (HMMA latency 23 cycles, issue one per ~9).
+__device__ __forceinline__ void mma_tf32_ordered(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <int NT>
+__device__ __forceinline__ void mma_step(float (&c)[NT][4], const float (&a)[4], const float (&b)[NT][2]) {
+  uint32_t ah[4], al[4], bh[NT][2], bl[NT][2];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) tf32_split(a[q], ah[q], al[q]);
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    tf32_split(b[j][0], bh[j][0], bl[j][0]);
+    tf32_split(b[j][1], bh[j][1], bl[j][1]);
+  }
+#pragma unroll
+  for (int j = 0; j < NT; ++j) mma_tf32_ordered(c[j], al, bh[j][0], bh[j][1]);      // small terms first
+#pragma unroll
+  for (int j = 0; j < NT; ++j) mma_tf32_ordered(c[j], ah, bl[j][0], bl[j][1]);
+#pragma unroll
+  for (int j = 0; j < NT; ++j) mma_tf32_ordered(c[j], ah, bh[j][0], bh[j][1]);
+}
+
+// data gradient: 16 requested input columns (row block mt) x NT column blocks of 8 tile rows from nt0
+template <int NT>
+__device__ __forceinline__ void mma_dgrad_task(const FusedOp& op, float* arena, const float* Ws, const int* tab, int RP,
+                                               int zero_row, int mt, int nt0, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const int O = op.O, n_dx = op.n_dx;
+  const int m_lo = mt * 16 + g, m_hi = m_lo + 8;
+  const bool v_lo = m_lo < n_dx, v_hi = m_hi < n_dx;
+  const float* w_lo = Ws + op.w_off + (v_lo ? tab[op.dxk_tab + m_lo] : 0) * O + t;
+  const float* w_hi = Ws + op.w_off + (v_hi ? tab[op.dxk_tab + m_hi] : 0) * O + t;
+  const int* dz_rows = tab + op.dz_tab + t;
+  float c[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+  const float* bcol = arena + nt0 * 8 + g;
+#pragma unroll 2
+  for (int o0 = 0; o0 < O; o0 += 8) {
+    const bool pa = o0 + t < O, pb = o0 + t + 4 < O;
+    const float a[4] = {(pa && v_lo) ? w_lo[o0] : 0.f, (pa && v_hi) ? w_hi[o0] : 0.f,
+                        (pb && v_lo) ? w_lo[o0 + 4] : 0.f, (pb && v_hi) ? w_hi[o0 + 4] : 0.f};
+    const float* pa_ = bcol + (pa ? dz_rows[o0] : zero_row) * RP;
+    const float* pb_ = bcol + (pb ? dz_rows[o0 + 4] : zero_row) * RP;
+    float b[NT][2];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { b[j][0] = pa_[j * 8]; b[j][1] = pb_[j * 8]; }
+    mma_step<NT>(c, a, b);
+  }
+  const bool gated = op.gate_tab >= 0;
+  float* out_lo = arena + (v_lo ? tab[op.dx_tab + m_lo] : zero_row) * RP;
+  float* out_hi = arena + (v_hi ? tab[op.dx_tab + m_hi] : zero_row) * RP;
+  const float* g_lo = arena + ((gated && v_lo) ? tab[op.gate_tab + m_lo] : zero_row) * RP;
+  const float* g_hi = arena + ((gated && v_hi) ? tab[op.gate_tab + m_hi] : zero_row) * RP;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int r = (nt0 + j) * 8 + 2 * t;
+    if (r < RP) {
+      float2 lo = make_float2(c[j][0], c[j][1]), hi = make_float2(c[j][2], c[j][3]);
+      if (gated) {
+        const float2 gl = *reinterpret_cast<const float2*>(g_lo + r), gh = *reinterpret_cast<const float2*>(g_hi + r);
+        lo.x = gl.x > 0.f ? lo.x : 0.f; lo.y = gl.y > 0.f ? lo.y : 0.f;
+        hi.x = gh.x > 0.f ? hi.x : 0.f; hi.y = gh.y > 0.f ? hi.y : 0.f;
+      }
+      if (v_lo) *reinterpret_cast<float2*>(out_lo + r) = lo;
+      if (v_hi) *reinterpret_cast<float2*>(out_hi + r) = hi;
+    }
+  }
+}
+
+// weight gradient: 16 input features (row block mt) x NT column blocks of 8 output features from nt0, summed over the
+// tile's RP rows; the block goes straight into this CTA's partial row (stored on the CTA's first tile, load-add-store
+// afterwards)
+template <int NT>
+__device__ __forceinline__ void mma_wgrad_task(const FusedOp& op, const float* arena, const int* tab, int RP, int zero_row,
+                                               int mt, int nt0, int lane, float* part, bool first_tile) {
+  const int g = lane >> 2, t = lane & 3;
+  const int K = op.K, O = op.O;
+  const int k_lo = mt * 16 + g, k_hi = k_lo + 8;
+  const float* x_lo = arena + (k_lo < K ? tab[op.in_tab + k_lo] : zero_row) * RP + t;
+  const float* x_hi = arena + (k_hi < K ? tab[op.in_tab + k_hi] : zero_row) * RP + t;
+  const float* dz[NT];
+  float c[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int o = (nt0 + j) * 8 + g;
+    dz[j] = arena + (o < O ? tab[op.dz_tab + o] : zero_row) * RP + t;
+    c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
+  }
+  const int full_end = RP & ~7;
+#pragma unroll 2
+  for (int r0 = 0; r0 < full_end; r0 += 8) {
+    const float a[4] = {x_lo[r0], x_hi[r0], x_lo[r0 + 4], x_hi[r0 + 4]};
+    float b[NT][2];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { b[j][0] = dz[j][r0]; b[j][1] = dz[j][r0 + 4]; }
+    mma_step<NT>(c, a, b);
+  }
+  if (full_end < RP) {                                       // RP is a multiple of 4: a last step of 4 rows
+    const float a[4] = {x_lo[full_end], x_hi[full_end], 0.f, 0.f};
+    float b[NT][2];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { b[j][0] = dz[j][full_end]; b[j][1] = 0.f; }
+    mma_step<NT>(c, a, b);
+  }
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int o = (nt0 + j) * 8 + 2 * t;
+    if (o < O) {
+      if (k_lo < K) {
+        float2* d = reinterpret_cast<float2*>(part + op.w_off + k_lo * O + o);
+        float2 v = make_float2(c[j][0], c[j][1]);
+        if (!first_tile) { const float2 old = __ldcg(d); v.x += old.x; v.y += old.y; }
+        *d = v;
+      }
+      if (k_hi < K) {
+        float2* d = reinterpret_cast<float2*>(part + op.w_off + k_hi * O + o);
+        float2 v = make_float2(c[j][2], c[j][3]);
+        if (!first_tile) { const float2 old = __ldcg(d); v.x += old.x; v.y += old.y; }
+        *d = v;
+      }
+    }
+  }
+}
+
+// backward phase of one layer on the tensor cores: weight-gradient tasks (the long ones) first, then the data-gradient
+// tasks, handed to the warps through the phase's work counter.  A task = one 16-row block x up to kMmaNT column blocks
+// (balanced group sizes; the exact count is a template parameter, so no tensor-core instruction is predicated).
+constexpr int kMmaNT = 6;
+#define V2V_MMA_DISPATCH(n, CALL)                 \
+  switch (n) {                                    \
+    case 1: { constexpr int NT_ = 1; CALL; break; } \
+    case 2: { constexpr int NT_ = 2; CALL; break; } \
+    case 3: { constexpr int NT_ = 3; CALL; break; } \
+    case 4: { constexpr int NT_ = 4; CALL; break; } \
+    case 5: { constexpr int NT_ = 5; CALL; break; } \
+    default: { constexpr int NT_ = 6; CALL; break; } \
+  }
+__device__ __forceinline__ void mma_bwd_phase(const FusedOp& op, int op_idx, float* arena, const float* Ws, const int* tab,
+                                              int RP, int zero_row, int tid, int my_bias, float& bacc, int* ctr, float* part,
+                                              bool first_tile) {
+  bias_grad(op, op_idx, arena, tab, RP, my_bias, bacc);
+  __syncwarp();
+  const int lane = tid & 31;
+  // weight gradient: K / 16 row blocks x O / 8 column blocks; data gradient: n_dx / 16 row blocks x RP / 8 column blocks
+  const int wM = (op.K + 15) >> 4, wN = (op.O + 7) >> 3;
+  const int wNg = (wN + kMmaNT - 1) / kMmaNT, wNper = (wN + wNg - 1) / wNg;
+  const int n_w = wM * wNg;
+  const int dM = (op.n_dx + 15) >> 4, dN = (RP + 7) >> 3;
+  const int dNg = (dN + kMmaNT - 1) / kMmaNT, dNper = (dN + dNg - 1) / dNg;
+  const int n_d = dM * dNg;
+  for (;;) {
+    int task = warp_next(ctr, lane);
+    if (task >= n_w + n_d) break;
+    if (task < n_w) {
+      const int mt = task / wNg, nt0 = (task - mt * wNg) * wNper;
+      V2V_MMA_DISPATCH(min(wNper, wN - nt0), mma_wgrad_task<NT_>(op, arena, tab, RP, zero_row, mt, nt0, lane, part, first_tile));
+    } else {
+      task -= n_w;
+      const int mt = task / dNg, nt0 = (task - mt * dNg) * dNper;
+      V2V_MMA_DISPATCH(min(dNper, dN - nt0), mma_dgrad_task<NT_>(op, arena, Ws, tab, RP, zero_row, mt, nt0, lane));
+    }
+  }
+}
+#undef V2V_MMA_DISPATCH
+
 __device__ long long* g_fused_trace = nullptr;       // optional per-phase clock trace of CTA 0 (profiling aid)
 
-template <int NMAX, bool SLOT>
+// MMA: 0 = every contraction on the FP32 pipe, 1 = backward contractions (weight and data gradients) on the tensor cores
+// (shared weights only)
+template <int NMAX, bool SLOT, int MMA>
 __global__ void __launch_bounds__(kFusedThreads, 1)
 fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__ params, const float* __restrict__ node,
                    const float* __restrict__ edge, const uint32_t* __restrict__ in_mask,
@@ -542,7 +762,7 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
 #pragma unroll
   for (int s = 0; s < kFusedBlkPerThread; ++s) {
     const int b = tid + s * kFusedThreads;
-    my_blk[s] = (!SLOT && train && b < P->n_blocks) ? P->blk_info[b] : 0;
+    my_blk[s] = (!SLOT && MMA == 0 && train && b < P->n_blocks) ? P->blk_info[b] : 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) wacc[s][i] = 0.f;
   }
@@ -649,7 +869,9 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
         }
         case FOP_AGG: agg_phase<NMAX, SLOT>(op, arena, tab, mask_s, RP, N, TG, TGp, tid); break;
         case FOP_LOSS: loss_phase<SLOT>(P, arena, tab, hl_s, RP, ng, inv_cnt, tid); break;
-        case FOP_BWD: bwd_phase<SLOT>(op, oi, arena, Wop, tab, RP, P->zero_row, tid, my_blk, wacc, my_bias, bacc, dWs, &dx_ctr[oi & 1], G, TGp, part, tile == (int)blockIdx.x); break;
+        case FOP_BWD:
+          if (MMA != 0) mma_bwd_phase(op, oi, arena, Wop, tab, RP, P->zero_row, tid, my_bias, bacc, &dx_ctr[oi & 1], part, tile == (int)blockIdx.x);
+          else bwd_phase<SLOT>(op, oi, arena, Wop, tab, RP, P->zero_row, tid, my_blk, wacc, my_bias, bacc, dWs, &dx_ctr[oi & 1], G, TGp, part, tile == (int)blockIdx.x); break;
         default: break;
       }
       if (trace) trace[((oi + 1) * kFusedWarps + warp) * 2] = clock64();
@@ -668,7 +890,9 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
 
   if (train) {
     float* dst = partial + (size_t)blockIdx.x * (n_params + kFusedPartialTail);
-    if (!SLOT) {
+    if (!SLOT && MMA != 0) {            // the weight gradients went to the partial row phase by phase
+      if (my_bias >= 0) dst[ops[my_bias >> 16].b_off + (my_bias & 0xffff)] = bacc;
+    } else if (!SLOT) {
 #pragma unroll
       for (int s = 0; s < kFusedBlkPerThread; ++s) {
         const int b = tid + s * kFusedThreads;
@@ -973,6 +1197,7 @@ size_t fused_smem_bytes(const FusedProgram& p) {
   words += p.n_small;
   words += 2 * (size_t)p.wstage_floats;
   words += (size_t)p.n_rows * p.RP;
+  words += 4;                                         // the tensor-core phases read up to 4 floats past the last arena row
   return words * 4;
 }
 
@@ -1002,7 +1227,7 @@ int fused_pick_tg(const FusedShape& s, int B, int train) {
 
 int fused_grid(const FusedProgram& p, int B) { return std::max(1, std::min(ceil_div(B, p.TG), sm_count())); }
 
-template <int NMAX, bool SLOT>
+template <int NMAX, bool SLOT, int MMA>
 static int fused_launch_t(const FusedProgram& ph, const FusedProgram* prog_dev, const float* params, const float* node,
                           const float* edge, const uint32_t* in_mask, const uint32_t* out_mask, const float* y, float* q_out,
                           float* partial_dev, float* head_loss, int B, int grid, cudaStream_t st) {
@@ -1010,7 +1235,7 @@ static int fused_launch_t(const FusedProgram& ph, const FusedProgram* prog_dev, 
   const float inv_cnt = 1.f / ((float)B * (float)ph.CH);
   static size_t smem_set = 0;                  // per instantiation (NMAX): every kernel needs its own opt-in
   if (smem > smem_set) {
-    V2V_CHECK_CUDA(cudaFuncSetAttribute(fused_brain_kernel<NMAX, SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    V2V_CHECK_CUDA(cudaFuncSetAttribute(fused_brain_kernel<NMAX, SLOT, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
   cudaLaunchConfig_t lc{};
@@ -1023,7 +1248,7 @@ static int fused_launch_t(const FusedProgram& ph, const FusedProgram* prog_dev, 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   lc.attrs = attr;
   lc.numAttrs = 1;
-  V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, fused_brain_kernel<NMAX, SLOT>, prog_dev, params, node, edge, in_mask, out_mask, y, q_out,
+  V2V_CHECK_CUDA(cudaLaunchKernelEx(&lc, fused_brain_kernel<NMAX, SLOT, MMA>, prog_dev, params, node, edge, in_mask, out_mask, y, q_out,
                                     partial_dev, head_loss, B, inv_cnt));
   return launch_status("fused_brain_kernel");
 }
@@ -1033,14 +1258,38 @@ int fused_launch(const FusedProgram& ph, const FusedProgram* prog_dev, const flo
                  float* partial_dev, float* head_loss, int B, int grid, cudaStream_t st) {
 #define V2V_FUSED_ARGS ph, prog_dev, params, node, edge, in_mask, out_mask, y, q_out, partial_dev, head_loss, B, grid, st
   if (ph.G > 1) {                                        // per-slot weights (the reference's model; N <= 8 here)
-    if (ph.N <= 4) return fused_launch_t<4, true>(V2V_FUSED_ARGS);
-    return fused_launch_t<8, true>(V2V_FUSED_ARGS);
+    if (ph.N <= 4) return fused_launch_t<4, true, 0>(V2V_FUSED_ARGS);
+    return fused_launch_t<8, true, 0>(V2V_FUSED_ARGS);
   }
-  if (ph.N <= 4) return fused_launch_t<4, false>(V2V_FUSED_ARGS);
-  if (ph.N <= 8) return fused_launch_t<8, false>(V2V_FUSED_ARGS);
-  if (ph.N <= 20) return fused_launch_t<20, false>(V2V_FUSED_ARGS);
-  return fused_launch_t<32, false>(V2V_FUSED_ARGS);
+  const int mma = fused_get_mma();
+#define V2V_FUSED_BY_N(M)                                                  \
+  do {                                                                     \
+    if (ph.N <= 4) return fused_launch_t<4, false, M>(V2V_FUSED_ARGS);     \
+    if (ph.N <= 8) return fused_launch_t<8, false, M>(V2V_FUSED_ARGS);     \
+    if (ph.N <= 20) return fused_launch_t<20, false, M>(V2V_FUSED_ARGS);   \
+    return fused_launch_t<32, false, M>(V2V_FUSED_ARGS);                   \
+  } while (0)
+  if (mma == 1) V2V_FUSED_BY_N(1);
+  V2V_FUSED_BY_N(0);
+#undef V2V_FUSED_BY_N
 #undef V2V_FUSED_ARGS
+}
+
+// Which pipe runs the backward contractions of the shared-weight kernel: 0 FP32 pipe, 1 tensor cores.
+// Process-wide (the choice does not change any result beyond rounding); V2V_FUSED_MMA overrides the default at first use.
+static int g_fused_mma = -1;
+int fused_get_mma() {
+  if (g_fused_mma < 0) {
+    int m = kFusedMmaDefault;
+    if (const char* e = getenv("V2V_FUSED_MMA")) m = atoi(e);
+    g_fused_mma = (m < 0 || m > 1) ? kFusedMmaDefault : m;
+  }
+  return g_fused_mma;
+}
+int fused_set_mma(int mode) {
+  V2V_REQUIRE(mode >= 0 && mode <= 1, "fused_set_mma: mode %d outside [0,1]", mode);
+  g_fused_mma = mode;
+  return 0;
 }
 
 int fused_set_trace(long long* dev_buf) {

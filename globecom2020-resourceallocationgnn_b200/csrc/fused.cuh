@@ -89,6 +89,10 @@ int fused_launch(const FusedProgram& prog_host, const FusedProgram* prog_dev, co
                  float* partial_dev, float* head_loss, int B, int grid, cudaStream_t st);
 int fused_grid(const FusedProgram& p, int B);
 int fused_set_trace(long long* dev_buf);      // dev_buf: >= kFusedMaxOps + 1 entries, or nullptr to disable
+// backward contractions of the shared-weight kernel: 0 = FP32 pipe, 1 = tensor cores (mma.sync TF32, 3 passes per product)
+constexpr int kFusedMmaDefault = 0;
+int fused_get_mma();
+int fused_set_mma(int mode);
 
 // Per-CTA partial rows are kFusedPartialTail floats longer than the parameter vector: the tail carries the CTA's
 // per-head Huber sums, so that loss and gradient leave through the same reduction (no atomics, no memset).

@@ -215,6 +215,12 @@ int v2v_brain_tc_debug(v2v_brain* b, const float* node_dev, const float* edge_de
 /* Profiling aid: lane 0 of every warp of CTA 0 writes clock64() into dev_buf[(phase*12 + warp)*2 + {0: work
  * done, 1: barrier released}] for its first tile (dev_buf >= 49*12*2 entries, device memory); NULL disables. */
 int v2v_fused_set_trace(long long* dev_buf);
+/* Which pipe runs the backward contractions (weight and data gradients of a.W1 + b.W2 + c.W3 and of the decision MLP:
+ * BS_brain.py:44-51, :176-200 under :218-223) of the fused shared-weight fp32 kernel: 0 = FP32 pipe (FFMA), 1 = tensor
+ * cores (mma.sync m16n8k8 TF32, three passes per product = fp32-grade products, fp32 accumulation).  The forward always
+ * runs in plain fp32.  Process-wide; the environment variable V2V_FUSED_MMA sets the initial value. */
+int v2v_fused_set_mma(int mode);
+int v2v_fused_get_mma(void);
 /* Same query from a configuration alone (host-only, no device needed). */
 int v2v_fused_plan(const v2v_brain_config* cfg, int B, int train, int* info8);
 /* update_target_model (BS_brain.py:237-239) */
