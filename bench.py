@@ -335,7 +335,7 @@ def run_engine_arm(a):
             node, edge, adj = synth_numpy(B, N, rng, a.sparse)
             yh = rng.normal(0, 1, (B, N, CH)).astype(np.float32)
             host.append(({"Node_Input": node, "Edge_Input": edge, "Adjacency_Matrix": adj}, {"Decide_Output": yh}))
-        for i in range(3):
+        for i in range(max(a.warmup, 3)):
             brain.train_dnn(host[i % 8][0], host[i % 8][1], B)
         k_e2e = max(20, min(a.steps, 200))
         barrier()

@@ -14,6 +14,7 @@
 
 #include <map>
 
+#include <atomic>
 #include "fused.cuh"
 #include "host_stage.cuh"
 #include "tc_forward.cuh"

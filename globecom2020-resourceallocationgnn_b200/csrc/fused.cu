@@ -567,18 +567,29 @@ __device__ __forceinline__ void mma_dgrad_task(const FusedOp& op, float* arena, 
 #pragma unroll
   for (int j = 0; j < NT; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
   const float* bcol = arena + nt0 * 8 + g;
-#pragma unroll 2
-  for (int o0 = 0; o0 < O; o0 += 8) {
+  // operands of step s + 1 are loaded before the tensor-core instructions of step s are issued (register double buffer)
+  auto load = [&](int o0, float (&a)[4], float (&b)[NT][2]) {
     const bool pa = o0 + t < O, pb = o0 + t + 4 < O;
-    const float a[4] = {(pa && v_lo) ? w_lo[o0] : 0.f, (pa && v_hi) ? w_hi[o0] : 0.f,
-                        (pb && v_lo) ? w_lo[o0 + 4] : 0.f, (pb && v_hi) ? w_hi[o0 + 4] : 0.f};
+    a[0] = (pa && v_lo) ? w_lo[o0] : 0.f; a[1] = (pa && v_hi) ? w_hi[o0] : 0.f;
+    a[2] = (pb && v_lo) ? w_lo[o0 + 4] : 0.f; a[3] = (pb && v_hi) ? w_hi[o0 + 4] : 0.f;
     const float* pa_ = bcol + (pa ? dz_rows[o0] : zero_row) * RP;
     const float* pb_ = bcol + (pb ? dz_rows[o0 + 4] : zero_row) * RP;
-    float b[NT][2];
 #pragma unroll
     for (int j = 0; j < NT; ++j) { b[j][0] = pa_[j * 8]; b[j][1] = pb_[j * 8]; }
-    mma_step<NT>(c, a, b);
+  };
+  float a0[4], b0[NT][2];
+  load(0, a0, b0);
+#pragma unroll 2
+  for (int o0 = 8; o0 < O; o0 += 8) {
+    float a1[4], b1[NT][2];
+    load(o0, a1, b1);
+    mma_step<NT>(c, a0, b0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a0[q] = a1[q];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { b0[j][0] = b1[j][0]; b0[j][1] = b1[j][1]; }
   }
+  mma_step<NT>(c, a0, b0);
   const bool gated = op.gate_tab >= 0;
   float* out_lo = arena + (v_lo ? tab[op.dx_tab + m_lo] : zero_row) * RP;
   float* out_hi = arena + (v_hi ? tab[op.dx_tab + m_hi] : zero_row) * RP;
@@ -619,37 +630,50 @@ __device__ __forceinline__ void mma_wgrad_task(const FusedOp& op, const float* a
     dz[j] = arena + (o < O ? tab[op.dz_tab + o] : zero_row) * RP + t;
     c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
   }
-  const int full_end = RP & ~7;
+  // the CTA's later tiles add to what its earlier tiles left in the partial row: fetch those values now, use them at the end
+  float2 old_lo[NT], old_hi[NT];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int o = (nt0 + j) * 8 + 2 * t;
+    old_lo[j] = old_hi[j] = make_float2(0.f, 0.f);
+    if (!first_tile && o < O) {
+      if (k_lo < K) old_lo[j] = __ldcg(reinterpret_cast<const float2*>(part + op.w_off + k_lo * O + o));
+      if (k_hi < K) old_hi[j] = __ldcg(reinterpret_cast<const float2*>(part + op.w_off + k_hi * O + o));
+    }
+  }
+  // operands of step s + 1 are loaded before the tensor-core instructions of step s are issued (register double buffer);
+  // RP is a multiple of 4: the last step may hold 4 rows
+  auto load = [&](int r0, float (&a)[4], float (&b)[NT][2]) {
+    const bool full = r0 + 8 <= RP;
+    a[0] = x_lo[r0]; a[1] = x_hi[r0];
+    a[2] = full ? x_lo[r0 + 4] : 0.f; a[3] = full ? x_hi[r0 + 4] : 0.f;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { b[j][0] = dz[j][r0]; b[j][1] = full ? dz[j][r0 + 4] : 0.f; }
+  };
+  float a0[4], b0[NT][2];
+  load(0, a0, b0);
 #pragma unroll 2
-  for (int r0 = 0; r0 < full_end; r0 += 8) {
-    const float a[4] = {x_lo[r0], x_hi[r0], x_lo[r0 + 4], x_hi[r0 + 4]};
-    float b[NT][2];
+  for (int r0 = 8; r0 < RP; r0 += 8) {
+    float a1[4], b1[NT][2];
+    load(r0, a1, b1);
+    mma_step<NT>(c, a0, b0);
 #pragma unroll
-    for (int j = 0; j < NT; ++j) { b[j][0] = dz[j][r0]; b[j][1] = dz[j][r0 + 4]; }
-    mma_step<NT>(c, a, b);
-  }
-  if (full_end < RP) {                                       // RP is a multiple of 4: a last step of 4 rows
-    const float a[4] = {x_lo[full_end], x_hi[full_end], 0.f, 0.f};
-    float b[NT][2];
+    for (int q = 0; q < 4; ++q) a0[q] = a1[q];
 #pragma unroll
-    for (int j = 0; j < NT; ++j) { b[j][0] = dz[j][full_end]; b[j][1] = 0.f; }
-    mma_step<NT>(c, a, b);
+    for (int j = 0; j < NT; ++j) { b0[j][0] = b1[j][0]; b0[j][1] = b1[j][1]; }
   }
+  mma_step<NT>(c, a0, b0);
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
     const int o = (nt0 + j) * 8 + 2 * t;
     if (o < O) {
       if (k_lo < K) {
         float2* d = reinterpret_cast<float2*>(part + op.w_off + k_lo * O + o);
-        float2 v = make_float2(c[j][0], c[j][1]);
-        if (!first_tile) { const float2 old = __ldcg(d); v.x += old.x; v.y += old.y; }
-        *d = v;
+        *d = make_float2(c[j][0] + old_lo[j].x, c[j][1] + old_lo[j].y);
       }
       if (k_hi < K) {
         float2* d = reinterpret_cast<float2*>(part + op.w_off + k_hi * O + o);
-        float2 v = make_float2(c[j][2], c[j][3]);
-        if (!first_tile) { const float2 old = __ldcg(d); v.x += old.x; v.y += old.y; }
-        *d = v;
+        *d = make_float2(c[j][2] + old_hi[j].x, c[j][3] + old_hi[j].y);
       }
     }
   }
@@ -658,15 +682,20 @@ __device__ __forceinline__ void mma_wgrad_task(const FusedOp& op, const float* a
 // backward phase of one layer on the tensor cores: weight-gradient tasks (the long ones) first, then the data-gradient
 // tasks, handed to the warps through the phase's work counter.  A task = one 16-row block x up to kMmaNT column blocks
 // (balanced group sizes; the exact count is a template parameter, so no tensor-core instruction is predicated).
-constexpr int kMmaNT = 6;
+#ifndef V2V_MMA_NT
+#define V2V_MMA_NT 6
+#endif
+constexpr int kMmaNT = V2V_MMA_NT;
 #define V2V_MMA_DISPATCH(n, CALL)                 \
   switch (n) {                                    \
     case 1: { constexpr int NT_ = 1; CALL; break; } \
-    case 2: { constexpr int NT_ = 2; CALL; break; } \
-    case 3: { constexpr int NT_ = 3; CALL; break; } \
-    case 4: { constexpr int NT_ = 4; CALL; break; } \
-    case 5: { constexpr int NT_ = 5; CALL; break; } \
-    default: { constexpr int NT_ = 6; CALL; break; } \
+    case 2: { constexpr int NT_ = kMmaNT >= 2 ? 2 : kMmaNT; CALL; break; } \
+    case 3: { constexpr int NT_ = kMmaNT >= 3 ? 3 : kMmaNT; CALL; break; } \
+    case 4: { constexpr int NT_ = kMmaNT >= 4 ? 4 : kMmaNT; CALL; break; } \
+    case 5: { constexpr int NT_ = kMmaNT >= 5 ? 5 : kMmaNT; CALL; break; } \
+    case 6: { constexpr int NT_ = kMmaNT >= 6 ? 6 : kMmaNT; CALL; break; } \
+    case 7: { constexpr int NT_ = kMmaNT >= 7 ? 7 : kMmaNT; CALL; break; } \
+    default: { constexpr int NT_ = kMmaNT; CALL; break; } \
   }
 __device__ __forceinline__ void mma_bwd_phase(const FusedOp& op, int op_idx, float* arena, const float* Ws, const int* tab,
                                               int RP, int zero_row, int tid, int my_bias, float& bacc, int* ctr, float* part,
@@ -684,6 +713,9 @@ __device__ __forceinline__ void mma_bwd_phase(const FusedOp& op, int op_idx, flo
   for (;;) {
     int task = warp_next(ctr, lane);
     if (task >= n_w + n_d) break;
+#ifdef V2V_MMA_DGRAD_FIRST
+    task = task < n_d ? task + n_w : task - n_d;
+#endif
     if (task < n_w) {
       const int mt = task / wNg, nt0 = (task - mt * wNg) * wNper;
       V2V_MMA_DISPATCH(min(wNper, wN - nt0), mma_wgrad_task<NT_>(op, arena, tab, RP, zero_row, mt, nt0, lane, part, first_tile));

@@ -90,7 +90,7 @@ int fused_launch(const FusedProgram& prog_host, const FusedProgram* prog_dev, co
 int fused_grid(const FusedProgram& p, int B);
 int fused_set_trace(long long* dev_buf);      // dev_buf: >= kFusedMaxOps + 1 entries, or nullptr to disable
 // backward contractions of the shared-weight kernel: 0 = FP32 pipe, 1 = tensor cores (mma.sync TF32, 3 passes per product)
-constexpr int kFusedMmaDefault = 0;
+constexpr int kFusedMmaDefault = 1;
 int fused_get_mma();
 int fused_set_mma(int mode);
 

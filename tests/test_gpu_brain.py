@@ -147,8 +147,56 @@ def test_forward_backward_vs_live_oracle(v2v, N, S, per_slot, B, kind):
                                             (4, 3, 256, True), (4, 3, 1, True), (4, 3, 5, True), (4, 3, 3000, True),
                                             (7, 2, 333, True), (8, 3, 64, True), (2, 1, 9, True)])
 def test_fused_kernel_matches_layered_kernels(v2v, N, S, B, per_slot):
+    try:
+        for mma in ((0, 1) if not per_slot else (1,)):
+            _fused_vs_layered(v2v, N, S, B, per_slot, mma)
+    finally:
+        assert v2v.load_library().v2v_fused_set_mma(1) == 0     # the default
+
+
+@pytest.mark.parametrize("N,S,B", [(20, 2, 1024), (20, 3, 2100), (4, 3, 64), (9, 1, 50), (32, 2, 200), (20, 2, 8192)])
+def test_tensor_core_backward_matches_fp32_pipe(v2v, N, S, B):
+    """Backward contractions on the tensor cores (mma.sync TF32, three passes per product) against the same kernel with
+    every contraction on the FP32 pipe: identical forward and loss (bit for bit), gradients to 1e-5 of their scale --
+    also when a CTA owns several tiles (its later tiles add to the partial row its earlier tiles wrote)."""
+    lib = v2v.load_library()
+    rng = np.random.default_rng(N + S + B)
+    brain = v2v.BS(N, 3, 1, 16, 1, 4, stages=S, per_slot=False, max_batch=B, data_parallel=False, seed=5)
+    node, edge, adj, _ = O.synth_batch(B, N, rng)
+    nd, ed, ad = (torch.from_numpy(t.astype(np.float32)).cuda() for t in (node, edge, adj))
+    im, om, _ = v2v.pack_adjacency(ad)
+    p0 = brain.get_flat_params(0) + rng.normal(0, 0.02, brain.get_flat_params(0).shape).astype(np.float32)
+    q = None
+    res = {}
+    try:
+        assert lib.v2v_fused_set_mma(2) != 0 and lib.v2v_fused_set_mma(-1) != 0      # only 0 and 1 exist
+        for mma in (0, 1):
+            assert lib.v2v_fused_set_mma(mma) == 0
+            brain.set_flat_params(p0, 0)
+            for w in (3, 4):
+                brain.set_flat_params(np.zeros_like(p0), w)
+            v2v._lib.check(lib.v2v_brain_set_iterations(brain._handle, 0))
+            if q is None:
+                brain.set_tensor_core(0)
+                q = brain.forward_device(nd, ed, in_mask=im)
+                y = q + torch.from_numpy(rng.normal(0, 1.0, tuple(q.shape)).astype(np.float32)).cuda()
+            hl = brain.train_step_device(nd, ed, im, om, None, y).cpu().numpy()
+            res[mma] = (hl, brain.get_flat_params(2))
+    finally:
+        assert lib.v2v_fused_set_mma(1) == 0
+    assert np.array_equal(res[0][0], res[1][0])                  # the forward and the Huber head do not change
+    g0, g1 = res[0][1], res[1][1]
+    assert np.isfinite(g1).all()
+    assert rel_err(g1, g0) <= 1e-5
+    assert np.array_equal(g1 == 0, g0 == 0)                      # dead parameters (stage-1 neighbour rows) stay exactly zero
+
+
+def _fused_vs_layered(v2v, N, S, B, per_slot, mma):
     """The one-launch fused network (shared weights, and per-slot weights up to N = 8) against the layer-by-layer
     kernels: forward to 1e-5, gradients, one Adam step."""
+    # mma: which pipe runs the backward contractions of the shared-weight kernel (0 FP32 pipe, 1 tensor cores, mma.sync
+    # TF32 in three passes per product); the forward is plain fp32 in both, so q and the loss must not move at all
+    assert v2v.load_library().v2v_fused_set_mma(mma) == 0 and v2v.load_library().v2v_fused_get_mma() == mma
     rng = np.random.default_rng(N * 100 + S * 10 + B)
     brain = v2v.BS(N, 3, 1, 16, 1, 4, stages=S, per_slot=per_slot, max_batch=B, data_parallel=False, seed=9)
     info = brain.fused_info(B)
