@@ -5,7 +5,9 @@
 
 Mnemonics (sm_100a): UTCHMMA = tcgen05.mma (kind::tf32 / kind::f16), UTCBAR = tcgen05.commit -> mbarrier, LDTM / STTM =
 tcgen05.ld / tcgen05.st (tensor memory <-> registers), UBLKCP = cp.async.bulk (1-D TMA copy), SYNCS = mbarrier ops,
-FADD2 / FFMA2 = packed fp32, HMMA / IMMA would be the legacy mma.sync path (expected: none)."""
+FADD2 / FFMA2 = packed fp32, HMMA = mma.sync (register-operand tensor-core instruction: only the backward contractions of
+the fp32 fused kernel use it, HMMA.1688.F32.TF32 in three passes per product -- csrc/fused.cu explains why tcgen05 cannot
+serve that kernel), IMMA: none."""
 import collections
 import os
 import re
