@@ -88,8 +88,32 @@ def brain_point(B, N, S=2, dtype="f32", per_slot=False):
     return us, info
 
 
+def brain_f32_section(quick):
+    """The fp32 shared-weight brain alone (``--brain-f32``: re-measures this section after a change of the fused kernel),
+    with the backward contractions on the tensor cores (the default) and on the FP32 pipe side by side."""
+    lib = v2v.load_library()
+    print("\n# brain fwd + Huber + bwd + Adam (2 stages, shared weights, fp32): graphs/s on one GPU; backward contractions on the")
+    print("# tensor cores (mma.sync TF32, 3 passes: the default) | on the FP32 pipe (V2V_FUSED_MMA=0)")
+    print(f"{'N':>4} {'B':>6} {'us/step':>9} {'graphs/s':>12} {'fp32-pipe us':>13}  path")
+    for N in (8, 16, 20, 32, 64):
+        for B in ((64, 1024, 8192) if quick else (64, 256, 1024, 4096, 8192, 32768)):
+            if N > 32 and B > 8192:
+                continue
+            lib.v2v_fused_set_mma(1)
+            us, info = brain_point(B, N)
+            us0 = float("nan")
+            if info["capable"]:
+                lib.v2v_fused_set_mma(0)
+                us0, _ = brain_point(B, N)
+                lib.v2v_fused_set_mma(1)
+            path = f"fused, {info['graphs_per_tile']} graphs/tile" if info["capable"] else "layer-by-layer kernels"
+            print(f"{N:4d} {B:6d} {us:9.1f} {B / us * 1e6:12.0f} {us0:13.1f}  {path}", flush=True)
+
+
 def main():
     quick = "--quick" in sys.argv
+    if "--brain-f32" in sys.argv:
+        return brain_f32_section(quick)
     Ns = [8, 16, 20, 32, 64, 128, 256]
     Bs = [64, 1024, 8192, 32768] if quick else [64, 256, 1024, 4096, 8192, 32768]
     print(f"# aggregation kernel sweep, fp32, F=16, reference-dense adjacency (E=N(N-2)), one B200, peak {PEAK} GB/s (measured)")
@@ -113,15 +137,7 @@ def main():
         nbytes, us_dep, us_ind = agg_point(B, 20, torch.float32, sparse=2)
         print(f"  20 {B:6d} {nbytes / 1e6:10.2f} {us_dep:8.2f} {nbytes / us_dep / 1e3 / PEAK:8.3f} {us_ind:8.2f} "
               f"{nbytes / us_ind / 1e3 / PEAK:8.3f}  TMA fast path, E=40")
-    print("\n# brain fwd + Huber + bwd + Adam (2 stages, shared weights, fp32): graphs/s on one GPU")
-    print(f"{'N':>4} {'B':>6} {'us/step':>9} {'graphs/s':>12}  path")
-    for N in (8, 16, 20, 32, 64):
-        for B in ((64, 1024, 8192) if quick else (64, 256, 1024, 4096, 8192, 32768)):
-            if N > 32 and B > 8192:
-                continue
-            us, info = brain_point(B, N)
-            path = f"fused, {info['graphs_per_tile']} graphs/tile" if info["capable"] else "layer-by-layer kernels"
-            print(f"{N:4d} {B:6d} {us:9.1f} {B / us * 1e6:12.0f}  {path}", flush=True)
+    brain_f32_section(quick)
     print("\n# brain fwd + Huber + bwd + Adam, BASELINE configs[2] form: 3 stages, shared weights, bf16 operands on tcgen05 (csrc/tc_train.cu)")
     print(f"{'N':>4} {'B':>6} {'us/step':>9} {'graphs/s':>12}  path")
     for N in (8, 20, 32):
