@@ -499,8 +499,7 @@ __device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* 
 //   weight grad dW[k][o]  = sum_r in[k][r] dz[o][r]             M = k,  N = o,               reduction over r
 // A warp task is MT x NT blocks of 16 x 8 outputs: every loaded value is split once and used by MT (or NT) blocks, which
 // is what keeps the split arithmetic (5 integer/float instructions per value) below the tensor pipe's time.  Every output
-// element has one owner and a fixed summation order (deterministic).  Columns r >= RP of the last column block read the
-// next arena row (finite values, never stored).
+// element has one owner and a fixed summation order (deterministic).
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
 #if V2V_TF32_SPLIT_RN
@@ -567,6 +566,9 @@ __device__ __forceinline__ void mma_dgrad_task(const FusedOp& op, float* arena, 
 #pragma unroll
   for (int j = 0; j < NT; ++j) c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.f;
   const float* bcol = arena + nt0 * 8 + g;
+  // RP is a multiple of 4, not of 8: in the tile's last column block the lanes of columns >= RP read column RP - 1 instead
+  // (their results are never stored; reading past the row would touch a row another warp may be writing)
+  const int last_off = min((nt0 + NT - 1) * 8 + g, RP - 1) - (nt0 * 8 + g);
   // operands of step s + 1 are loaded before the tensor-core instructions of step s are issued (register double buffer)
   auto load = [&](int o0, float (&a)[4], float (&b)[NT][2]) {
     const bool pa = o0 + t < O, pb = o0 + t + 4 < O;
@@ -575,7 +577,8 @@ __device__ __forceinline__ void mma_dgrad_task(const FusedOp& op, float* arena, 
     const float* pa_ = bcol + (pa ? dz_rows[o0] : zero_row) * RP;
     const float* pb_ = bcol + (pb ? dz_rows[o0 + 4] : zero_row) * RP;
 #pragma unroll
-    for (int j = 0; j < NT; ++j) { b[j][0] = pa_[j * 8]; b[j][1] = pb_[j * 8]; }
+    for (int j = 0; j < NT - 1; ++j) { b[j][0] = pa_[j * 8]; b[j][1] = pb_[j * 8]; }
+    b[NT - 1][0] = pa_[last_off]; b[NT - 1][1] = pb_[last_off];
   };
   float a0[4], b0[NT][2];
   load(0, a0, b0);
@@ -1229,7 +1232,6 @@ size_t fused_smem_bytes(const FusedProgram& p) {
   words += p.n_small;
   words += 2 * (size_t)p.wstage_floats;
   words += (size_t)p.n_rows * p.RP;
-  words += 4;                                         // the tensor-core phases read up to 4 floats past the last arena row
   return words * 4;
 }
 
