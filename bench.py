@@ -295,6 +295,14 @@ def run_engine_arm(a):
         pool.append((nd, ed, im, om, y))
         del ad
     head_loss = torch.zeros(N, device=dev)
+    # the host-side batches of the end-to-end leg are prepared up front too, so that nothing but the calls themselves
+    # separates the two timed regions (generating them in between leaves the GPU idle for ~0.1 s)
+    host = []
+    if not a.no_e2e:
+        for i in range(8):
+            node, edge, adj = synth_numpy(B, N, rng, a.sparse)
+            yh = rng.normal(0, 1, (B, N, CH)).astype(np.float32)
+            host.append(({"Node_Input": node, "Edge_Input": edge, "Adjacency_Matrix": adj}, {"Decide_Output": yh}))
     torch.cuda.synchronize()
 
     def step(i):
@@ -330,11 +338,6 @@ def run_engine_arm(a):
     # ---- e2e: the reference-facing call with HOST buffers (BS.train_dnn), copies inside the timed region
     e2e = None
     if not a.no_e2e:
-        host = []
-        for i in range(8):
-            node, edge, adj = synth_numpy(B, N, rng, a.sparse)
-            yh = rng.normal(0, 1, (B, N, CH)).astype(np.float32)
-            host.append(({"Node_Input": node, "Edge_Input": edge, "Adjacency_Matrix": adj}, {"Decide_Output": yh}))
         for i in range(max(a.warmup, 3)):
             brain.train_dnn(host[i % 8][0], host[i % 8][1], B)
         k_e2e = max(20, min(a.steps, 200))

@@ -731,6 +731,47 @@ __device__ __forceinline__ void mma_bwd_phase(const FusedOp& op, int op_idx, flo
 }
 #undef V2V_MMA_DISPATCH
 
+// Shared weights: the tile's node / edge / target rows -> feature rows of the arena.  The three spans are contiguous in
+// global memory; with `bulk` one thread fetches them by bulk-async copies into arena rows that are dead at tile start (all
+// bytes in flight at once: one memory latency instead of one per round of a load loop) and the CTA transposes from shared
+// memory.  Kept out of line: inlined, its temporaries cost the phase loops ten registers.
+__device__ __noinline__ void load_tile_inputs(const FusedProgram* P, float* arena, const int* tab, const float* node,
+                                              const float* edge, const float* y, int g0, int valid_rows, bool bulk,
+                                              uint32_t parity, uint64_t* bar, int tid) {
+  const int N = P->N, RP = P->RP, Dn = P->Dn, De = P->De, CH = P->CH;
+  const float* nsrc = node + (size_t)g0 * N * Dn;
+  const float* esrc = edge + (size_t)g0 * N * De;
+  const float* ysrc = y ? y + (size_t)g0 * N * CH : nullptr;
+  if (bulk) {
+    float* stage = arena + (size_t)P->stage_row0 * RP;
+    if (tid == 0) {
+      fence_async_smem();                  // the rows were written by the previous tile's phases (generic proxy)
+      const uint32_t nb = (uint32_t)valid_rows * Dn * 4u, eb = (uint32_t)valid_rows * De * 4u;
+      const uint32_t yb = y ? (uint32_t)valid_rows * CH * 4u : 0u;
+      mbar_arrive_expect_tx(bar, nb + eb + yb);
+      bulk_g2s(stage, nsrc, nb, bar);
+      bulk_g2s(stage + RP * Dn, esrc, eb, bar);
+      if (y) bulk_g2s(stage + RP * (Dn + De), ysrc, yb, bar);
+    }
+    mbar_wait(bar, parity);                // one completion per tile
+    nsrc = stage; esrc = stage + RP * Dn; ysrc = stage + RP * (Dn + De);
+  }
+  for (int idx = tid; idx < RP * Dn; idx += kFusedThreads) {
+    const int r = idx / Dn, f = idx - r * Dn;
+    arena[(P->x0_row0 + f) * RP + r] = (r < valid_rows) ? nsrc[idx] : 0.f;
+  }
+  for (int idx = tid; idx < RP * De; idx += kFusedThreads) {
+    const int r = idx / De, f = idx - r * De;
+    arena[(P->x0_row0 + Dn + f) * RP + r] = (r < valid_rows) ? esrc[idx] : 0.f;
+  }
+  if (y) {
+    for (int idx = tid; idx < RP * CH; idx += kFusedThreads) {
+      const int r = idx / CH, c = idx - r * CH;
+      arena[tab[P->y_tab + c] * RP + r] = (r < valid_rows) ? ysrc[idx] : 0.f;
+    }
+  }
+}
+
 __device__ long long* g_fused_trace = nullptr;       // optional per-phase clock trace of CTA 0 (profiling aid)
 
 // MMA: 0 = every contraction on the FP32 pipe, 1 = backward contractions (weight and data gradients) on the tensor cores
@@ -762,10 +803,16 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
   const int wstage = SLOT ? P->wstage_floats : 0;
   float* arena = wbuf + 2 * wstage;
   __shared__ __align__(8) uint64_t wbar[2];
-  if (SLOT && tid == 0) {
+  if (tid == 0) {
     mbar_init(&wbar[0], 1); mbar_init(&wbar[1], 1);
     fence_mbar_init();
   }
+  // Shared weights: a tile's node / edge / target rows are three contiguous spans of global memory.  One thread fetches them
+  // with bulk-async copies into arena rows that are dead at tile start (all bytes in flight at once: one memory latency
+  // instead of one per round of a load loop), then the CTA transposes them into feature rows from shared memory.
+  const bool bulk_in = !SLOT && P->stage_row0 >= 0 && (N * Dn) % 4 == 0 && (N * De) % 4 == 0 && (!train || (N * CH) % 4 == 0) &&
+                       ((reinterpret_cast<uintptr_t>(node) | reinterpret_cast<uintptr_t>(edge) |
+                         (train ? reinterpret_cast<uintptr_t>(y) : (uintptr_t)0)) & 15u) == 0;
   float* part = (train && partial) ? partial + (size_t)blockIdx.x * (n_params + kFusedPartialTail) : nullptr;
 
   // programmatic dependent launch: everything up to griddepcontrol.wait overlaps the tail of the preceding kernel
@@ -831,24 +878,14 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
     const int ng = min(TG, B - g0);
     const int valid_rows = ng * N;
     __syncthreads();                         // previous tile fully consumed (and the prologue stores)
+    // adjacency bit masks: plain loads, issued first so that they are in flight together with the bulk copies below
+    for (int idx = tid; idx < TG * N; idx += kFusedThreads) {
+      mask_s[idx] = (idx < valid_rows) ? in_mask[(size_t)g0 * N + idx] : 0u;
+      if (train) mask_s[TG * N + idx] = (idx < valid_rows) ? out_mask[(size_t)g0 * N + idx] : 0u;
+    }
     if (!SLOT) {
-      const float* nsrc = node + (size_t)g0 * N * Dn;
-      for (int idx = tid; idx < RP * Dn; idx += kFusedThreads) {
-        const int r = idx / Dn, f = idx - r * Dn;
-        arena[(P->x0_row0 + f) * RP + r] = (r < valid_rows) ? nsrc[idx] : 0.f;
-      }
-      const float* esrc = edge + (size_t)g0 * N * De;
-      for (int idx = tid; idx < RP * De; idx += kFusedThreads) {
-        const int r = idx / De, f = idx - r * De;
-        arena[(P->x0_row0 + Dn + f) * RP + r] = (r < valid_rows) ? esrc[idx] : 0.f;
-      }
-      if (train) {
-        const float* ysrc = y + (size_t)g0 * N * CH;
-        for (int idx = tid; idx < RP * CH; idx += kFusedThreads) {
-          const int r = idx / CH, c = idx - r * CH;
-          arena[tab[P->y_tab + c] * RP + r] = (r < valid_rows) ? ysrc[idx] : 0.f;
-        }
-      }
+      load_tile_inputs(P, arena, tab, node, edge, train ? y : nullptr, g0, valid_rows, bulk_in,
+                       (uint32_t)((tile - (int)blockIdx.x) / (int)gridDim.x) & 1u, &wbar[0], tid);
     } else {                                 // slot-major rows: node (g, n) -> row n * TGp + g
       const float* nsrc = node + (size_t)g0 * N * Dn;
       for (int idx = tid; idx < TG * N * Dn; idx += kFusedThreads) {
@@ -870,10 +907,6 @@ fused_brain_kernel(const FusedProgram* __restrict__ P, const float* __restrict__
           arena[tab[P->y_tab + c] * RP + g * row_g + n * row_n] = (g < ng) ? ysrc[idx] : 0.f;
         }
       }
-    }
-    for (int idx = tid; idx < TG * N; idx += kFusedThreads) {
-      mask_s[idx] = (idx < valid_rows) ? in_mask[(size_t)g0 * N + idx] : 0u;
-      if (train) mask_s[TG * N + idx] = (idx < valid_rows) ? out_mask[(size_t)g0 * N + idx] : 0u;
     }
     __syncthreads();
     // profiling aid: lane 0 of every warp of CTA 0 records [phase][warp] = {work done, barrier released}
@@ -1103,6 +1136,7 @@ int fused_build_program(const FusedShape& s, int TG, int train, FusedProgram* ou
   for (int j = 0; j < 4; ++j) {
     const int l = S + j;
     mrows[j] = b.fresh(widths[j]);
+    if (j == 0) P->stage_row0 = (!slot && Dn + De + s.CH <= widths[0]) ? mrows[0][0] : -1;
     gemm_in[l] = (j == 0) ? cat({nodeR, h[S - 1], a[S - 1]}) : mrows[j - 1];
     V2V_REQUIRE((int)gemm_in[l].size() == s.layer_K[l], "fused path: layer %d input width mismatch", l);
     FusedOp* g = b.add_op();

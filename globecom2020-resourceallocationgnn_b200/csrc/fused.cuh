@@ -60,6 +60,8 @@ struct FusedProgram {
   int G, TGp, row_g, row_n;
   int wstage_floats;      // per-slot weights: floats of ONE of the two shared-memory weight buffers the layers' spans are
                           // streamed through (bulk-async copies, one layer ahead); 0: read the weights from global memory
+  int stage_row0;         // shared weights: first of the arena rows (dead at tile start) that receive the tile's contiguous
+                          // node | edge | target spans by bulk-async copy before they are transposed into feature rows; -1: none
   FusedOp ops[kFusedMaxOps];
   int tab[kFusedMaxTab];
   // block b -> op index, k0, o0 (packed: op<<16 | k0<<8 | o0), bias slot -> op<<16 | o
