@@ -41,3 +41,20 @@ def test_last_error_and_argument_validation_without_gpu(v2v):
     assert rc != 0 and b"n_seg" in lib.v2v_last_error()
     rc = lib.v2v_dense_fwd(1, None, None, None, 0, None, None, 1, 4, 3, 16, 0, None)
     assert rc != 0 and b"G must be" in lib.v2v_last_error()
+
+
+def test_backward_pipe_switch_is_a_host_side_setting(v2v):
+    """v2v_fused_set_mma / v2v_fused_get_mma (which pipe runs the backward contractions of the shared-weight fp32 kernel):
+    process-wide, validated, default = tensor cores unless V2V_FUSED_MMA says otherwise.  No device needed."""
+    import os
+    lib = v2v.load_library()
+    default = lib.v2v_fused_get_mma()
+    assert default == (int(os.environ["V2V_FUSED_MMA"]) if os.environ.get("V2V_FUSED_MMA") in ("0", "1") else 1)
+    try:
+        for mode in (0, 1):
+            assert lib.v2v_fused_set_mma(mode) == 0 and lib.v2v_fused_get_mma() == mode
+        for bad in (-1, 2, 7):
+            assert lib.v2v_fused_set_mma(bad) != 0 and b"outside [0,1]" in lib.v2v_last_error()
+            assert lib.v2v_fused_get_mma() == 1            # a rejected value leaves the setting alone
+    finally:
+        assert lib.v2v_fused_set_mma(default) == 0
