@@ -378,6 +378,12 @@ def run_engine_arm(a):
             "l2": f"rotating pool of {R} distinct device-resident input batches ({R * per_batch / 2**20:.0f} MiB "
                   f"> 126 MiB L2); roofline loop rotates over buffer sets > L2 as well",
             "final_loss": loss_now,
+            "arithmetic": ("bf16 contraction operands on tcgen05, fp32 accumulation, fp32 master weights / loss / Adam"
+                           if a.dtype == "bf16" else
+                           ("fp32 throughout; the backward contractions of the fused kernel run on the tensor cores as "
+                            "three TF32 passes per product (hi/lo operand splits, fp32 accumulation: fp32-grade, gradients "
+                            "within 3e-6 of the FP32-pipe form), the forward on the FP32 pipe"
+                            if lib.v2v_fused_get_mma() == 1 and not a.per_slot else "fp32 throughout, FP32 pipe")),
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof, "cpu_baseline": cpu, "peaks": peaks, "predict": predict,
         }
