@@ -492,8 +492,9 @@ __device__ __forceinline__ void bwd_phase(const FusedOp& op, int op_idx, float* 
 // operands read as zeros, scratch/tc_probe_mn.cu) and hi/lo copies of a whole tile do not fit shared memory, so these
 // phases use the register-operand tensor-core instruction instead: mma.sync m16n8k8 TF32 (SASS HMMA.1688.F32.TF32; measured
 // on B200, scratch/hmma_probe.cu: 23 cycles dependent, one per 2.17 cycles per SM) with every product done in three passes
-// (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi; hi = TF32 round-to-nearest, lo = the rounded remainder: the dropped lo*lo term and the
-// two roundings are each <= 2^-24 of |a||b|, i.e. fp32-grade products; fp32 accumulation).  A fragment element is ONE
+// (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi; hi = the upper 19 bits, lo = the exact remainder, which the tensor core reads through
+// its upper 19 bits: the dropped lo*lo term and the truncation of the two lo operands are each <= 2^-20 of |a||b| -- emulated
+// in tests/test_properties.py -- i.e. fp32-grade dot products; fp32 accumulation).  A fragment element is ONE
 // scalar shared-memory load whatever the orientation of the operand, so both gradients of a layer are the same routine:
 //   data grad   dx[kq][r] = gate * sum_o W[kq][o] dz[o][r]      M = kq, N = r (tile rows),   reduction over o
 //   weight grad dW[k][o]  = sum_r in[k][r] dz[o][r]             M = k,  N = o,               reduction over r

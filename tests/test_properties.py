@@ -87,3 +87,31 @@ def test_host_packer_is_an_exact_encoding_of_any_binary_adjacency(v2v, B, N, see
     dec_in = ((im[:, :, None] >> bits[None, None, :]) & 1).transpose(0, 2, 1)
     dec_out = (om[:, :, None] >> bits[None, None, :]) & 1
     assert np.array_equal(dec_in, adj.astype(np.uint32)) and np.array_equal(dec_out, adj.astype(np.uint32))
+
+
+def _tf32_trunc(x):
+    """The upper 19 bits of an fp32 value (what the TF32 datapath reads), as fp32."""
+    return (np.asarray(x, np.float32).view(np.uint32) & np.uint32(0xffffe000)).view(np.float32)
+
+
+@FAST
+@given(K=st.integers(1, 160), seed=st.integers(0, 2**31 - 1), scale=st.sampled_from([1e-3, 1.0, 1e3]))
+def test_three_pass_tf32_products_are_fp32_grade(K, seed, scale):
+    """The arithmetic of the tensor-core backward (csrc/fused.cu, tf32_split + the three passes), emulated exactly:
+    hi = upper 19 bits, lo = x - hi (exact in fp32), lo read by the tensor core through its upper 19 bits, the three
+    products a_lo*b_hi + a_hi*b_lo + a_hi*b_hi of 11-bit significands are exact.  What is lost per product is the
+    lo*lo term and the truncation of the two lo operands: at most 3 * 2^-20 of |a||b|, i.e. a dot product carries
+    the same order of error as one accumulated in fp32 -- three orders of magnitude below single-pass TF32."""
+    rng = np.random.default_rng(seed)
+    a = (rng.normal(size=K) * scale).astype(np.float32)
+    b = rng.normal(size=K).astype(np.float32)
+    ah, bh = _tf32_trunc(a), _tf32_trunc(b)
+    al, bl = _tf32_trunc(a - ah), _tf32_trunc(b - bh)
+    assert np.array_equal((a - ah).astype(np.float64), a.astype(np.float64) - ah.astype(np.float64))    # lo is exact
+    f8 = np.float64
+    three = (al.astype(f8) * bh + ah.astype(f8) * bl + ah.astype(f8) * bh).sum()
+    exact = (a.astype(f8) * b.astype(f8)).sum()
+    bound = np.abs(a.astype(f8) * b.astype(f8)).sum()
+    assert abs(three - exact) <= 3 * 2.0 ** -20 * bound
+    one = (ah.astype(f8) * bh).sum()                                           # single-pass TF32 for scale
+    assert abs(one - exact) <= 2 * 2.0 ** -10 * bound
